@@ -1,0 +1,701 @@
+// gmm_api.cu — the C ABI of include/gmm.h: context, operators, EM loop,
+// model-order reduction.  Host orchestration in C++, compute in the CUDA
+// kernels of kernels_simt.cuh / kernels_tc.cuh, cross-GPU reduction with one
+// ncclAllReduce of the packed sufficient statistics per iteration.
+//
+// Reference being replaced: gaussian.cu:289-960 (the OpenMP-thread-per-GPU body
+// of main()).  There is no CPU fallback: every compute entry point needs a
+// CUDA device of compute capability 10.x.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gmm.h"
+#include "host_math.h"
+#include "kernels_simt.cuh"
+#include "kernels_tc.cuh"
+
+namespace gmm {
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(GMM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+
+// ---- NCCL, loaded lazily so that the library imports without it -----------
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+static NcclApi& nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (api.handle) {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+            api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+            api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy && api.GetErrorString;
+        }
+    }
+    return api;
+}
+#define NCCL_TRY(expr)                                                                         \
+    do {                                                                                       \
+        ncclResult_t r_ = (expr);                                                              \
+        if (r_ != ncclSuccess)                                                                 \
+            return fail(GMM_ERR_NCCL, std::string(#expr) + ": " + nccl().GetErrorString(r_));  \
+    } while (0)
+
+struct PhaseTimer {          // replaces cudaTimer_t / profile_t (gaussian.cu:33-106)
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    double total_ms = 0;
+};
+
+}  // namespace gmm
+
+using namespace gmm;
+
+struct gmm_ctx {
+    int device = 0, n = 0, D = 0, Kmax = 0, F = 0;
+    long long n_global = 0, offset = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 148;
+    // events
+    float* d_x_aos = nullptr;    // [n][D]  as supplied (TMA source of the tensor path)
+    float* d_x_soa = nullptr;    // [D][n]  transpose for the SIMT kernels
+    // responsibilities, cluster-major [Kmax][n]
+    float* d_memb = nullptr;
+    float* d_memb_saved = nullptr;   // best configuration during gmm_fit
+    // parameters
+    float* d_epack = nullptr;    // SIMT E-step parameters [Kmax][epack_stride]
+    float* h_epack = nullptr;    // pinned staging
+    double* d_stats = nullptr;   // [Kmax*F + 1]
+    double* h_stats = nullptr;   // pinned
+    double* d_shift = nullptr;   // [32]
+    double shift[GMM_MAX_DIMENSIONS] = {0};
+    bool have_shift = false;
+    // host copy of the current parameters (all arrays sized for Kmax)
+    std::vector<float> hN, hpi, hconst, havgvar, hmeans, hR, hRinv;
+    clusters_t host{};
+    int cur_K = 0;
+    bool memb_valid = false;     // d_memb holds the responsibilities of the current parameters
+    // communication
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    // options
+    int path = GMM_PATH_AUTO;
+    int verbose = 0;
+    int host_threads = 1;
+    // profile
+    PhaseTimer t_estep, t_mstep, t_reduce, t_fused;
+    double host_const_ms = 0, memcpy_ms = 0;
+    long long iterations = 0;
+    TcState* tc = nullptr;       // tensor-core path state (kernels_tc.cuh)
+};
+
+namespace gmm {
+
+static void timer_begin(gmm_ctx* c, PhaseTimer& t) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, c->stream);
+    t.pending.push_back({a, b});
+}
+static void timer_end(gmm_ctx* c, PhaseTimer& t) { cudaEventRecord(t.pending.back().second, c->stream); }
+static void timer_collect(PhaseTimer& t) {          // call after a stream sync
+    for (auto& p : t.pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) t.total_ms += ms;
+        cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+    }
+    t.pending.clear();
+}
+static void collect_all(gmm_ctx* c) {
+    timer_collect(c->t_estep); timer_collect(c->t_mstep); timer_collect(c->t_reduce); timer_collect(c->t_fused);
+}
+
+static void bind_host(gmm_ctx* c) {
+    c->host.N = c->hN.data(); c->host.pi = c->hpi.data(); c->host.constant = c->hconst.data();
+    c->host.avgvar = c->havgvar.data(); c->host.means = c->hmeans.data(); c->host.R = c->hR.data();
+    c->host.Rinv = c->hRinv.data(); c->host.memberships = nullptr;
+}
+
+static void copy_params(clusters_t* dst, const clusters_t* src, int K, int D) {
+    std::memcpy(dst->N, src->N, sizeof(float) * K);
+    std::memcpy(dst->pi, src->pi, sizeof(float) * K);
+    std::memcpy(dst->constant, src->constant, sizeof(float) * K);
+    std::memcpy(dst->avgvar, src->avgvar, sizeof(float) * K);
+    std::memcpy(dst->means, src->means, sizeof(float) * (size_t)K * D);
+    std::memcpy(dst->R, src->R, sizeof(float) * (size_t)K * D * D);
+    std::memcpy(dst->Rinv, src->Rinv, sizeof(float) * (size_t)K * D * D);
+}
+
+static bool use_tensor_path(const gmm_ctx* c, int K) {
+    if (c->path == GMM_PATH_SIMT) return false;
+    return tc_supported(c->D, K);
+}
+// GMM_PATH_TENSOR never degrades silently.
+static int check_path(const gmm_ctx* c, int K) {
+    if (c->path == GMM_PATH_TENSOR && !tc_supported(c->D, K))
+        return fail(GMM_ERR_ARG, "GMM_PATH_TENSOR requested but the tcgen05 kernels do not cover this (D, K)");
+    return GMM_OK;
+}
+
+// Upload the current host parameters in the form the E-step kernels consume
+// (gaussian.cu:446-452 / 935-941 upload the seven raw arrays; here the E-step
+// operand is pre-packed on the host once per iteration).
+static int upload_params(gmm_ctx* c, int K) {
+    if (int rc = check_path(c, K)) return rc;
+    auto t0 = std::chrono::steady_clock::now();
+    if (use_tensor_path(c, K)) {
+        int rc = tc_upload_params(c->tc, &c->host, K, c->stream);
+        if (rc) return rc;
+    }
+    if (!use_tensor_path(c, K) || c->path == GMM_PATH_AUTO) {
+        // the SIMT pack is tiny; AUTO keeps it current so gmm_estep can always fall back to a supported kernel
+        build_epack(K, c->D, &c->host, c->h_epack);
+        CUDA_TRY(cudaMemcpyAsync(c->d_epack, c->h_epack, sizeof(float) * (size_t)K * epack_stride(c->D),
+                                 cudaMemcpyHostToDevice, c->stream));
+    }
+    c->cur_K = K;
+    c->memcpy_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return GMM_OK;
+}
+
+// ---- kernel dispatch -------------------------------------------------------
+template <int D>
+static void launch_estep_simt_d(gmm_ctx* c, int K) {
+    const int blocks = (c->n + kEstepThreads - 1) / kEstepThreads;
+    estep_simt_kernel<D><<<blocks, kEstepThreads, 0, c->stream>>>(c->d_x_soa, c->n, K, c->d_epack, c->d_memb,
+                                                                 c->d_stats + (size_t)K * c->F);
+}
+static int launch_estep_simt(gmm_ctx* c, int K) {
+    if (c->n == 0) return GMM_OK;
+    switch (c->D) {
+#define GMM_CASE(d) case d: launch_estep_simt_d<d>(c, K); break;
+        GMM_CASE(1) GMM_CASE(2) GMM_CASE(3) GMM_CASE(4) GMM_CASE(5) GMM_CASE(6) GMM_CASE(7) GMM_CASE(8)
+        GMM_CASE(9) GMM_CASE(10) GMM_CASE(11) GMM_CASE(12) GMM_CASE(13) GMM_CASE(14) GMM_CASE(15) GMM_CASE(16)
+        GMM_CASE(17) GMM_CASE(18) GMM_CASE(19) GMM_CASE(20) GMM_CASE(21) GMM_CASE(22) GMM_CASE(23) GMM_CASE(24)
+        GMM_CASE(25) GMM_CASE(26) GMM_CASE(27) GMM_CASE(28) GMM_CASE(29) GMM_CASE(30) GMM_CASE(31) GMM_CASE(32)
+#undef GMM_CASE
+        default: return fail(GMM_ERR_ARG, "unsupported dimension count");
+    }
+    CUDA_TRY(cudaGetLastError());
+    return GMM_OK;
+}
+
+template <int JMAX, int CPT>
+static int launch_mstep_simt_t(gmm_ctx* c, int K) {
+    constexpr int FP = 16 * JMAX, KT = 16 * CPT, GS = KT + 2;
+    const size_t smem = sizeof(double) * (size_t)(kMstepTE * FP + kMstepTE * GS + kMstepTE * GMM_MAX_DIMENSIONS) +
+                        sizeof(short) * 2 * FP;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(mstep_simt_kernel<JMAX, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int gx = c->num_sms;
+    int per = (c->n + gx - 1) / gx;
+    per = (per + kMstepTE - 1) / kMstepTE * kMstepTE;
+    if (per < kMstepTE) per = kMstepTE;
+    gx = (c->n + per - 1) / per;
+    dim3 grid(gx, (K + KT - 1) / KT);
+    mstep_simt_kernel<JMAX, CPT><<<grid, kMstepThreads, smem, c->stream>>>(c->d_x_soa, c->n, c->D, K, c->d_memb,
+                                                                           c->d_shift, c->d_stats, per);
+    CUDA_TRY(cudaGetLastError());
+    return GMM_OK;
+}
+static int launch_mstep_simt(gmm_ctx* c, int K) {
+    if (c->n == 0) return GMM_OK;
+    const int F = c->F;
+    const int cpt = K <= 16 ? 1 : (K <= 32 ? 2 : 4);
+    if (F <= 48) {
+        if (cpt == 1) return launch_mstep_simt_t<3, 1>(c, K);
+        if (cpt == 2) return launch_mstep_simt_t<3, 2>(c, K);
+        return launch_mstep_simt_t<3, 4>(c, K);
+    } else if (F <= 160) {
+        if (cpt == 1) return launch_mstep_simt_t<10, 1>(c, K);
+        if (cpt == 2) return launch_mstep_simt_t<10, 2>(c, K);
+        return launch_mstep_simt_t<10, 4>(c, K);
+    } else if (F <= 336) {
+        if (cpt == 1) return launch_mstep_simt_t<21, 1>(c, K);
+        if (cpt == 2) return launch_mstep_simt_t<21, 2>(c, K);
+        return launch_mstep_simt_t<21, 4>(c, K);
+    } else {
+        if (cpt == 1) return launch_mstep_simt_t<36, 1>(c, K);
+        return launch_mstep_simt_t<36, 2>(c, K);
+    }
+}
+
+static int zero_stats(gmm_ctx* c, int K) {
+    CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(double) * ((size_t)K * c->F + 1), c->stream));
+    return GMM_OK;
+}
+
+// E-step on the current device parameters: responsibilities -> d_memb, local
+// log-likelihood added to stats[K*F].
+static int run_estep(gmm_ctx* c, int K) {
+    timer_begin(c, c->t_estep);
+    int rc = use_tensor_path(c, K) ? tc_launch_estep(c->tc, K, c->d_memb, c->d_stats + (size_t)K * c->F, c->stream)
+                                   : launch_estep_simt(c, K);
+    timer_end(c, c->t_estep);
+    c->memb_valid = (rc == GMM_OK);
+    return rc;
+}
+
+// M-step accumulation of the local statistics into stats[0 .. K*F).
+static int run_mstep_accumulate(gmm_ctx* c, int K) {
+    timer_begin(c, c->t_mstep);
+    int rc = use_tensor_path(c, K) ? tc_launch_mstep(c->tc, K, c->d_memb, c->d_stats, c->stream)
+                                   : launch_mstep_simt(c, K);
+    timer_end(c, c->t_mstep);
+    return rc;
+}
+
+// Sum the packed statistics over all ranks (replaces the four MPI_Allreduce of
+// gaussian.cu:516,566,605,658,741 and the OpenMP-master sums) and bring them
+// to the host.
+static int reduce_stats_to_host(gmm_ctx* c, int K) {
+    const size_t len = (size_t)K * c->F + 1;
+    timer_begin(c, c->t_reduce);
+    if (c->nranks > 1) {
+        ncclResult_t r = nccl().AllReduce(c->d_stats, c->d_stats, len, ncclDouble, ncclSum, c->comm, c->stream);
+        if (r != ncclSuccess) return fail(GMM_ERR_NCCL, std::string("ncclAllReduce: ") + nccl().GetErrorString(r));
+    }
+    timer_end(c, c->t_reduce);
+    CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(double) * len, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return GMM_OK;
+}
+
+static int finalize_and_upload(gmm_ctx* c, int K) {
+    auto t0 = std::chrono::steady_clock::now();
+    finalize_from_stats(c->h_stats, c->shift, K, c->D, &c->host, c->host_threads);
+    c->host_const_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return upload_params(c, K);
+}
+
+static int check_K(const gmm_ctx* c, int K, const char* who) {
+    if (!c) return fail(GMM_ERR_ARG, std::string(who) + ": null context");
+    if (K < 1 || K > c->Kmax) return fail(GMM_ERR_ARG, std::string(who) + ": K out of range");
+    return GMM_OK;
+}
+
+}  // namespace gmm
+
+// ===========================================================================
+extern "C" {
+
+const char* gmm_version(void) { return "cuda-gmm-mpi_b200 0.1 (sm_100a)"; }
+
+int gmm_create(gmm_ctx** out, int device, int n_local, int D, int Kmax, const float* events_aos,
+               long long n_global, long long offset) {
+    if (!out) return fail(GMM_ERR_ARG, "gmm_create: null out");
+    *out = nullptr;
+    if (D < 1 || D > GMM_MAX_DIMENSIONS) return fail(GMM_ERR_ARG, "gmm_create: D must be in [1,32] (gaussian.h:16)");
+    if (Kmax < 1 || Kmax > GMM_MAX_CLUSTERS) return fail(GMM_ERR_ARG, "gmm_create: Kmax must be in [1,512] (gaussian.h:10)");
+    if (n_local < 0 || (n_local > 0 && !events_aos)) return fail(GMM_ERR_ARG, "gmm_create: bad events");
+    if (n_global <= 0) n_global = n_local;
+    if (n_global < 1) return fail(GMM_ERR_ARG, "gmm_create: no events");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(GMM_ERR_CUDA, "ERROR: No CUDA capable GPUs detected (this engine has no CPU fallback).");
+    if (device < 0 || device >= ndev) return fail(GMM_ERR_ARG, "gmm_create: device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(GMM_ERR_CUDA, std::string("device '") + prop.name + "' is not sm_100 (B200); kernels are built for sm_100a only");
+
+    gmm_ctx* c = new gmm_ctx();
+    c->device = device; c->n = n_local; c->D = D; c->Kmax = Kmax; c->F = num_features(D);
+    c->n_global = n_global; c->offset = offset; c->num_sms = prop.multiProcessorCount;
+    const char* ht = getenv("GMM_HOST_THREADS");
+    c->host_threads = ht ? atoi(ht) : 8;
+    if (c->host_threads < 1) c->host_threads = 1;
+    c->hN.assign(Kmax, 0); c->hpi.assign(Kmax, 0); c->hconst.assign(Kmax, 0); c->havgvar.assign(Kmax, 0);
+    c->hmeans.assign((size_t)Kmax * D, 0); c->hR.assign((size_t)Kmax * D * D, 0); c->hRinv.assign((size_t)Kmax * D * D, 0);
+    bind_host(c);
+#define CREATE_TRY(expr)                                                                             \
+    do {                                                                                             \
+        cudaError_t e_ = (expr);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            int rc_ = fail(GMM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));        \
+            gmm_destroy(c);                                                                          \
+            return rc_;                                                                              \
+        }                                                                                            \
+    } while (0)
+    CREATE_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const size_t nmax = n_local > 0 ? (size_t)n_local : 1;
+    CREATE_TRY(cudaMalloc(&c->d_x_aos, sizeof(float) * nmax * D));
+    CREATE_TRY(cudaMalloc(&c->d_x_soa, sizeof(float) * nmax * D));
+    CREATE_TRY(cudaMalloc(&c->d_memb, sizeof(float) * nmax * Kmax));
+    CREATE_TRY(cudaMalloc(&c->d_epack, sizeof(float) * (size_t)Kmax * epack_stride(D)));
+    CREATE_TRY(cudaMallocHost(&c->h_epack, sizeof(float) * (size_t)Kmax * epack_stride(D)));
+    CREATE_TRY(cudaMalloc(&c->d_stats, sizeof(double) * ((size_t)Kmax * c->F + 1)));
+    CREATE_TRY(cudaMallocHost(&c->h_stats, sizeof(double) * ((size_t)Kmax * c->F + 1)));
+    CREATE_TRY(cudaMalloc(&c->d_shift, sizeof(double) * GMM_MAX_DIMENSIONS));
+    CREATE_TRY(cudaMemsetAsync(c->d_shift, 0, sizeof(double) * GMM_MAX_DIMENSIONS, c->stream));
+    if (n_local > 0) {
+        CREATE_TRY(cudaMemcpyAsync(c->d_x_aos, events_aos, sizeof(float) * (size_t)n_local * D, cudaMemcpyHostToDevice, c->stream));
+        dim3 blk(32, 8);
+        transpose_aos_to_soa_kernel<<<(n_local + 31) / 32, blk, 0, c->stream>>>(c->d_x_aos, c->d_x_soa, n_local, D);
+        CREATE_TRY(cudaGetLastError());
+    }
+    {
+        int rc = tc_create(&c->tc, c->d_x_aos, n_local, D, Kmax, c->num_sms, c->stream);
+        if (rc) { gmm_destroy(c); return rc; }
+    }
+    CREATE_TRY(cudaStreamSynchronize(c->stream));
+#undef CREATE_TRY
+    *out = c;
+    return GMM_OK;
+}
+
+void gmm_destroy(gmm_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    collect_all(c);
+    if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+    tc_destroy(c->tc);
+    cudaFree(c->d_x_aos); cudaFree(c->d_x_soa); cudaFree(c->d_memb); cudaFree(c->d_memb_saved);
+    cudaFree(c->d_epack); cudaFree(c->d_stats); cudaFree(c->d_shift);
+    if (c->h_epack) cudaFreeHost(c->h_epack);
+    if (c->h_stats) cudaFreeHost(c->h_stats);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int gmm_nccl_unique_id(char id_out[128]) {
+    if (!id_out) return fail(GMM_ERR_ARG, "gmm_nccl_unique_id: null");
+    if (!nccl().ok) return fail(GMM_ERR_NCCL, "libnccl.so.2 not found");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId id;
+    NCCL_TRY(nccl().GetUniqueId(&id));
+    std::memcpy(id_out, &id, 128);
+    return GMM_OK;
+}
+
+int gmm_comm_init(gmm_ctx* c, int nranks, int rank, const char id_in[128]) {
+    if (!c || nranks < 1 || rank < 0 || rank >= nranks) return fail(GMM_ERR_ARG, "gmm_comm_init: bad argument");
+    c->rank = rank; c->nranks = nranks;
+    if (nranks == 1) return GMM_OK;
+    if (!id_in) return fail(GMM_ERR_ARG, "gmm_comm_init: null id");
+    if (!nccl().ok) return fail(GMM_ERR_NCCL, "libnccl.so.2 not found");
+    CUDA_TRY(cudaSetDevice(c->device));
+    ncclUniqueId id;
+    std::memcpy(&id, id_in, 128);
+    NCCL_TRY(nccl().CommInitRank(&c->comm, nranks, id, rank));
+    return GMM_OK;
+}
+
+int gmm_comm_rank(const gmm_ctx* c, int* rank, int* nranks) {
+    if (!c) return fail(GMM_ERR_ARG, "gmm_comm_rank: null context");
+    if (rank) *rank = c->rank;
+    if (nranks) *nranks = c->nranks;
+    return GMM_OK;
+}
+
+int gmm_set_option(gmm_ctx* c, const char* key, double value) {
+    if (!c || !key) return fail(GMM_ERR_ARG, "gmm_set_option: bad argument");
+    const std::string k(key);
+    if (k == "path") {
+        const int p = (int)value;
+        if (p < GMM_PATH_AUTO || p > GMM_PATH_TENSOR) return fail(GMM_ERR_ARG, "gmm_set_option: bad path");
+        c->path = p;
+    } else if (k == "verbose") c->verbose = (int)value;
+    else if (k == "host_threads") c->host_threads = value < 1 ? 1 : (int)value;
+    else if (k == "write_memberships") { /* accepted; every E-step materialises memberships in this build */ }
+    else return fail(GMM_ERR_ARG, "gmm_set_option: unknown key '" + k + "'");
+    return GMM_OK;
+}
+
+// --- seeding ---------------------------------------------------------------
+int gmm_seed(gmm_ctx* c, int K, clusters_t* host_out) {
+    if (int rc = check_K(c, K, "gmm_seed")) return rc;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int D = c->D;
+    // packed: [sum x (D) | sum x^2 (D) | seed rows (K*D)] in double, reduced over ranks.
+    const size_t len = (size_t)2 * D + (size_t)K * D;
+    if (len > (size_t)c->Kmax * c->F + 1) return fail(GMM_ERR_STATE, "gmm_seed: stats buffer too small");
+    CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(double) * len, c->stream));
+    if (c->n > 0) {
+        dim3 grid(std::min(4 * c->num_sms, (c->n + 255) / 256), D);
+        column_moments_kernel<<<grid, 256, 0, c->stream>>>(c->d_x_soa, c->n, D, c->d_stats);
+        CUDA_TRY(cudaGetLastError());
+    }
+    // seed rows owned by this shard (evenly spaced events, gaussian.cu:110-120)
+    std::vector<double> rows((size_t)K * D, 0.0);
+    std::vector<float> tmp(D);
+    for (int k = 0; k < K; k++) {
+        const long long g = seed_event_index(k, K, c->n_global);
+        if (g >= c->offset && g < c->offset + c->n) {
+            CUDA_TRY(cudaMemcpyAsync(tmp.data(), c->d_x_aos + (size_t)(g - c->offset) * D, sizeof(float) * D,
+                                     cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            for (int d = 0; d < D; d++) rows[(size_t)k * D + d] = tmp[d];
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->d_stats + 2 * D, rows.data(), sizeof(double) * K * D, cudaMemcpyHostToDevice, c->stream));
+    if (c->nranks > 1) {
+        ncclResult_t r = nccl().AllReduce(c->d_stats, c->d_stats, len, ncclDouble, ncclSum, c->comm, c->stream);
+        if (r != ncclSuccess) return fail(GMM_ERR_NCCL, std::string("ncclAllReduce: ") + nccl().GetErrorString(r));
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(double) * len, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    std::vector<float> seed_rows((size_t)K * D);
+    for (size_t i = 0; i < seed_rows.size(); i++) seed_rows[i] = (float)c->h_stats[2 * D + i];
+    seed_from_moments(c->h_stats, c->h_stats + D, c->n_global, D, K, seed_rows.data(), &c->host);
+    // Statistics are accumulated about the global mean (DESIGN.md "shift").
+    for (int d = 0; d < D; d++) c->shift[d] = c->h_stats[d] / (double)c->n_global;
+    c->have_shift = true;
+    CUDA_TRY(cudaMemcpyAsync(c->d_shift, c->shift, sizeof(double) * D, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = tc_set_shift(c->tc, c->shift, c->stream)) return rc;
+    if (int rc = upload_params(c, K)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->memb_valid = false;
+    if (host_out) copy_params(host_out, &c->host, K, D);
+    return GMM_OK;
+}
+
+int gmm_set_clusters(gmm_ctx* c, int K, const clusters_t* in) {
+    if (int rc = check_K(c, K, "gmm_set_clusters")) return rc;
+    if (!in) return fail(GMM_ERR_ARG, "gmm_set_clusters: null clusters");
+    CUDA_TRY(cudaSetDevice(c->device));
+    copy_params(&c->host, in, K, c->D);
+    c->memb_valid = false;
+    if (int rc = upload_params(c, K)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return GMM_OK;
+}
+
+int gmm_get_clusters(gmm_ctx* c, int K, clusters_t* out, int with_memberships) {
+    if (int rc = check_K(c, K, "gmm_get_clusters")) return rc;
+    if (!out) return fail(GMM_ERR_ARG, "gmm_get_clusters: null clusters");
+    CUDA_TRY(cudaSetDevice(c->device));
+    copy_params(out, &c->host, K, c->D);
+    if (with_memberships) {
+        if (!out->memberships) return fail(GMM_ERR_ARG, "gmm_get_clusters: memberships requested but pointer is null");
+        if (!c->memb_valid) return fail(GMM_ERR_STATE, "gmm_get_clusters: no E-step has run for the current parameters");
+        if (c->n > 0)
+            CUDA_TRY(cudaMemcpyAsync(out->memberships, c->d_memb, sizeof(float) * (size_t)K * c->n, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    return GMM_OK;
+}
+
+int gmm_estep(gmm_ctx* c, int K, float* loglik_out) {
+    if (int rc = check_K(c, K, "gmm_estep")) return rc;
+    if (K != c->cur_K) return fail(GMM_ERR_STATE, "gmm_estep: parameters for this K have not been set");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t ll = (size_t)K * c->F;
+    CUDA_TRY(cudaMemsetAsync(c->d_stats + ll, 0, sizeof(double), c->stream));
+    if (int rc = run_estep(c, K)) return rc;
+    if (c->nranks > 1) {
+        ncclResult_t r = nccl().AllReduce(c->d_stats + ll, c->d_stats + ll, 1, ncclDouble, ncclSum, c->comm, c->stream);
+        if (r != ncclSuccess) return fail(GMM_ERR_NCCL, std::string("ncclAllReduce: ") + nccl().GetErrorString(r));
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->h_stats + ll, c->d_stats + ll, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    collect_all(c);
+    if (loglik_out) *loglik_out = (float)c->h_stats[ll];
+    return GMM_OK;
+}
+
+int gmm_mstep(gmm_ctx* c, int K) {
+    if (int rc = check_K(c, K, "gmm_mstep")) return rc;
+    if (!c->memb_valid || K != c->cur_K) return fail(GMM_ERR_STATE, "gmm_mstep: run gmm_estep first");
+    if (!c->have_shift) {      // parameters came from gmm_set_clusters without gmm_seed: zero shift is valid, just less conditioned
+        for (int d = 0; d < c->D; d++) c->shift[d] = 0.0;
+        c->have_shift = true;
+    }
+    CUDA_TRY(cudaSetDevice(c->device));
+    const double ll_keep = c->h_stats[(size_t)K * c->F];
+    CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(double) * (size_t)K * c->F, c->stream));
+    if (int rc = run_mstep_accumulate(c, K)) return rc;
+    if (int rc = reduce_stats_to_host(c, K)) return rc;
+    c->h_stats[(size_t)K * c->F] = ll_keep;
+    // gmm_mstep stops before constants_kernel: N, means, R only (gaussian.cu:538-687)
+    finalize_from_stats(c->h_stats, c->shift, K, c->D, &c->host, c->host_threads, /*with_constants=*/false);
+    collect_all(c);
+    return GMM_OK;
+}
+
+int gmm_constants(gmm_ctx* c, int K) {
+    if (int rc = check_K(c, K, "gmm_constants")) return rc;
+    CUDA_TRY(cudaSetDevice(c->device));
+    auto t0 = std::chrono::steady_clock::now();
+    constants_from_R(K, c->D, &c->host, c->host_threads);
+    c->host_const_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (int rc = upload_params(c, K)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return GMM_OK;
+}
+
+// One pass of the loop body of gaussian.cu:532-755 on the device-resident
+// responsibilities: M-step statistics -> all-reduce -> host normalisation and
+// constants -> parameter upload -> E-step.  The log-likelihood of the E-step
+// that produced the responsibilities rides in the packed buffer and is returned
+// through *prev_loglik.
+static int em_iteration(gmm_ctx* c, int K, float* prev_loglik) {
+    if (int rc = run_mstep_accumulate(c, K)) return rc;
+    if (int rc = reduce_stats_to_host(c, K)) return rc;
+    if (prev_loglik) *prev_loglik = (float)c->h_stats[(size_t)K * c->F];
+    if (int rc = finalize_and_upload(c, K)) return rc;    // gaussian.cu:611-622, 663-679, 698-708
+    if (int rc = zero_stats(c, K)) return rc;
+    if (int rc = run_estep(c, K)) return rc;              // gaussian.cu:713-714
+    c->iterations++;
+    return GMM_OK;
+}
+
+// Bring only the log-likelihood slot of the last E-step to the host (summed over ranks).
+static int reduce_loglik_to_host(gmm_ctx* c, int K, float* out) {
+    const size_t ll = (size_t)K * c->F;
+    if (c->nranks > 1) {
+        ncclResult_t r = nccl().AllReduce(c->d_stats + ll, c->d_stats + ll, 1, ncclDouble, ncclSum, c->comm, c->stream);
+        if (r != ncclSuccess) return fail(GMM_ERR_NCCL, std::string("ncclAllReduce: ") + nccl().GetErrorString(r));
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->h_stats + ll, c->d_stats + ll, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (out) *out = (float)c->h_stats[ll];
+    return GMM_OK;
+}
+
+int gmm_em_iterations(gmm_ctx* c, int K, int iters, float* loglik_out) {
+    if (int rc = check_K(c, K, "gmm_em_iterations")) return rc;
+    if (!c->memb_valid || K != c->cur_K) return fail(GMM_ERR_STATE, "gmm_em_iterations: run gmm_estep first");
+    if (!c->have_shift) { for (int d = 0; d < c->D; d++) c->shift[d] = 0.0; c->have_shift = true; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    for (int i = 0; i < iters; i++)
+        if (int rc = em_iteration(c, K, nullptr)) return rc;
+    if (int rc = reduce_loglik_to_host(c, K, loglik_out)) return rc;
+    collect_all(c);
+    return GMM_OK;
+}
+
+// The EM loop (gaussian.cu:487-755): initial E-step, then
+// while(iters < min_iters || (|change| > epsilon && iters < max_iters)).
+// The convergence test needs the log-likelihood of the E-step that just ran;
+// it rides in the same packed buffer as the M-step statistics, so when the
+// test can still go either way the next M-step accumulation is issued before
+// the test (and discarded if the loop ends there).
+int gmm_em(gmm_ctx* c, int K, int min_iters, int max_iters, float epsilon, float* loglik_out, int* iters_out) {
+    if (int rc = check_K(c, K, "gmm_em")) return rc;
+    if (K != c->cur_K) return fail(GMM_ERR_STATE, "gmm_em: parameters for this K have not been set (gmm_seed / gmm_set_clusters)");
+    if (!c->have_shift) { for (int d = 0; d < c->D; d++) c->shift[d] = 0.0; c->have_shift = true; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (epsilon < 0) epsilon = em_epsilon(c->D, c->n_global);
+    const size_t ll_idx = (size_t)K * c->F;
+    if (int rc = zero_stats(c, K)) return rc;
+    if (int rc = run_estep(c, K)) return rc;                 // initial E-step, gaussian.cu:487-523
+    float likelihood = 0, old_likelihood = 0, change = epsilon * 2;
+    int iters = 0;
+    for (;;) {
+        const bool must_continue = iters < min_iters;
+        const bool may_continue = iters < max_iters;
+        if (!must_continue && !may_continue) {               // the loop ends whatever the change is
+            if (int rc = reduce_loglik_to_host(c, K, &likelihood)) return rc;
+            break;
+        }
+        if (int rc = run_mstep_accumulate(c, K)) return rc;
+        if (int rc = reduce_stats_to_host(c, K)) return rc;
+        likelihood = (float)c->h_stats[ll_idx];
+        if (iters > 0) change = likelihood - old_likelihood;
+        if (!(must_continue || (std::fabs(change) > epsilon && may_continue))) break;   // gaussian.cu:532
+        old_likelihood = likelihood;
+        if (int rc = finalize_and_upload(c, K)) return rc;   // host normalisation + constants
+        if (int rc = zero_stats(c, K)) return rc;
+        if (int rc = run_estep(c, K)) return rc;             // gaussian.cu:713-714
+        iters++;
+        c->iterations++;
+        if (c->verbose > 1) std::printf("[gmm rank %d] K=%d iter %d\n", c->rank, K, iters);
+    }
+    collect_all(c);
+    if (loglik_out) *loglik_out = likelihood;
+    if (iters_out) *iters_out = iters;
+    return GMM_OK;
+}
+
+int gmm_get_profile(gmm_ctx* c, double out[8], int reset) {
+    if (!c || !out) return fail(GMM_ERR_ARG, "gmm_get_profile: bad argument");
+    cudaStreamSynchronize(c->stream);
+    collect_all(c);
+    out[0] = c->t_estep.total_ms; out[1] = c->t_mstep.total_ms; out[2] = c->host_const_ms;
+    out[3] = c->t_reduce.total_ms; out[4] = c->memcpy_ms; out[5] = c->t_fused.total_ms;
+    out[6] = (double)c->iterations; out[7] = 0;
+    if (reset) {
+        c->t_estep.total_ms = c->t_mstep.total_ms = c->t_reduce.total_ms = c->t_fused.total_ms = 0;
+        c->host_const_ms = c->memcpy_ms = 0; c->iterations = 0;
+    }
+    return GMM_OK;
+}
+
+// Model-order reduction loop (gaussian.cu:479-960).
+int gmm_fit(gmm_ctx* c, int K0, int target_K, int min_iters, int max_iters, clusters_t* saved, int* ideal_K,
+            float* min_rissanen_out) {
+    if (int rc = check_K(c, K0, "gmm_fit")) return rc;
+    if (target_K < 0 || target_K > K0) return fail(GMM_ERR_ARG, "target_num_clusters must be less than equal to num_clusters");
+    if (!saved) return fail(GMM_ERR_ARG, "gmm_fit: null saved clusters");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int D = c->D;
+    const int stop_number = target_K == 0 ? 1 : target_K;                  // gaussian.cu:177-181
+    if (int rc = gmm_seed(c, K0, nullptr)) return rc;
+    const float epsilon = em_epsilon(D, c->n_global);
+    float min_rissanen = 0;
+    int ideal = K0;
+    if (saved->memberships && !c->d_memb_saved && c->n > 0)
+        CUDA_TRY(cudaMalloc(&c->d_memb_saved, sizeof(float) * (size_t)c->n * c->Kmax));
+    for (int K = K0; K >= stop_number;) {
+        float likelihood; int iters;
+        if (int rc = gmm_em(c, K, min_iters, max_iters, epsilon, &likelihood, &iters)) return rc;
+        const float r = rissanen(likelihood, K, D, c->n_global);          // :826
+        if (c->verbose && c->rank == 0) std::printf("K=%d loglik=%e Rissanen Score: %e\n", K, likelihood, r);
+        if (K == K0 || (r < min_rissanen && target_K == 0) || K == target_K) {   // :839
+            min_rissanen = r;
+            ideal = K;
+            copy_params(saved, &c->host, K, D);
+            if (saved->memberships && c->n > 0)
+                CUDA_TRY(cudaMemcpyAsync(c->d_memb_saved, c->d_memb, sizeof(float) * (size_t)K * c->n, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        if (K > stop_number) {                                            // :860-950
+            K = reduce_order(&c->host, K, D, nullptr, nullptr, c->host_threads);
+            if (K < 1) break;
+            c->memb_valid = false;
+            if (int rc = upload_params(c, K)) return rc;
+        } else break;
+    }
+    if (saved->memberships && c->n > 0) {
+        CUDA_TRY(cudaMemcpyAsync(saved->memberships, c->d_memb_saved, sizeof(float) * (size_t)ideal * c->n, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (ideal_K) *ideal_K = ideal;
+    if (min_rissanen_out) *min_rissanen_out = min_rissanen;
+    return GMM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    p = entry.load_package()
+    if not os.path.exists(p.library_path()):
+        entry.build()
+    p.load_library()
+    return p
+
+
+@pytest.fixture(scope="session")
+def oracle64(pkg):
+    return entry.load_oracle("f64")
+
+
+@pytest.fixture(scope="session")
+def oracle32(pkg):
+    return entry.load_oracle("f32")
+
+
+def have_gpu():
+    try:
+        import ctypes
+        rt = ctypes.CDLL("libcudart.so.12")
+        n = ctypes.c_int(0)
+        return rt.cudaGetDeviceCount(ctypes.byref(n)) == 0 and n.value > 0
+    except OSError:
+        try:
+            import torch
+            return torch.cuda.is_available()
+        except Exception:
+            return False
+
+
+def gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def random_spd_params(pkg, K, D, rng, spread=4.0):
+    """Random, well-conditioned mixture parameters with consistent Rinv/constant."""
+    cl = pkg.Clusters(K, D)
+    cl.means[...] = rng.uniform(-spread, spread, size=(K, D)).astype(np.float32)
+    for k in range(K):
+        A = rng.standard_normal((D, D))
+        R = A @ A.T / D + 0.5 * np.eye(D)
+        cl.R[k] = R.astype(np.float32)
+    w = rng.dirichlet(np.full(K, 5.0))
+    cl.N[...] = (w * 1000).astype(np.float32)
+    cl.avgvar[...] = 0.01
+    return cl
+
+
+def assert_params_close(got, ref, K, rtol=1e-4):
+    """The parity bar of BASELINE.json: 1e-4 relative on means / covariances
+    (absolute floor scaled to each cluster's largest covariance entry)."""
+    np.testing.assert_allclose(got.N[:K], ref.N[:K], rtol=rtol, atol=1e-3)
+    np.testing.assert_allclose(got.pi[:K], ref.pi[:K], rtol=rtol, atol=1e-7)
+    mscale = max(1.0, float(np.abs(ref.means[:K]).max()))
+    np.testing.assert_allclose(got.means[:K], ref.means[:K], rtol=rtol, atol=rtol * mscale)
+    for k in range(K):
+        s = float(np.abs(ref.R[k]).max())
+        np.testing.assert_allclose(got.R[k], ref.R[k], rtol=rtol, atol=rtol * s, err_msg=f"R[{k}]")
+        si = float(np.abs(ref.Rinv[k]).max())
+        np.testing.assert_allclose(got.Rinv[k], ref.Rinv[k], rtol=10 * rtol, atol=10 * rtol * si, err_msg=f"Rinv[{k}]")
+    np.testing.assert_allclose(got.constant[:K], ref.constant[:K], rtol=rtol, atol=1e-3)

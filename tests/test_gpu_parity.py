@@ -1,0 +1,287 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through
+the C ABI, against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): 1e-4 relative on responsibilities (with an
+absolute floor of 1e-6), means and covariances; integer-exact final cluster count;
+log-likelihood 1e-5 relative (FP32 in the reference; the engine reduces it in
+double)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, random_spd_params, assert_params_close, gpu_count
+
+pytestmark = pytest.mark.gpu
+
+PATHS = ["simt", "auto"]
+
+
+def path_id(pkg, name):
+    return {"simt": pkg.PATH_SIMT, "auto": pkg.PATH_AUTO, "tensor": pkg.PATH_TENSOR}[name]
+
+
+def assert_memb_close(got, ref, rtol=1e-4, atol=1e-6):
+    np.testing.assert_allclose(got, ref, rtol=rtol, atol=atol)
+
+
+@pytest.fixture(scope="module")
+def loaded(pkg):
+    pkg.load_library()
+    return pkg
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("N,D,K", [(10_000, 4, 8), (5_003, 16, 32), (4_097, 24, 64), (1_000, 1, 3),
+                                   (777, 32, 5), (3_000, 7, 130), (33, 3, 2), (20_000, 24, 16)])
+def test_estep_parity(loaded, oracle64, path, N, D, K):
+    pkg = loaded
+    ev = pkg.synth.make_blobs(N, D, min(K, 8), seed=100 + D)
+    ref = random_spd_params(pkg, K, D, np.random.default_rng(D * 7 + K), spread=6.0)
+    ref.memberships = np.zeros((K, N), np.float32)
+    oracle64.constants(ref, K)
+    with pkg.Engine(ev, K) as eng:
+        eng.set_option("path", path_id(pkg, path))
+        eng.set_clusters(K, ref)
+        ll = eng.estep(K)
+        got = eng.get_clusters(K, with_memberships=True)
+    ll_ref = oracle64.estep(oracle64.transpose(ev), ref, K)
+    assert_memb_close(got.memberships, ref.memberships)
+    np.testing.assert_allclose(got.memberships.sum(0), 1.0, atol=1e-5)
+    assert abs(ll - ll_ref) <= 1e-5 * abs(ll_ref)
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("N,D,K", [(10_000, 4, 8), (5_003, 16, 32), (4_097, 24, 64), (1_000, 1, 3),
+                                   (777, 32, 5), (3_000, 7, 130), (33, 3, 2), (20_000, 24, 16)])
+def test_mstep_constants_parity(loaded, oracle64, path, N, D, K):
+    """gmm_mstep (N, means, R) then gmm_constants (Rinv, constant, pi) from the
+    SAME responsibilities as the oracle."""
+    pkg = loaded
+    ev = pkg.synth.make_blobs(N, D, min(K, 8), seed=200 + D)
+    ref = random_spd_params(pkg, K, D, np.random.default_rng(D * 11 + K), spread=6.0)
+    ref.memberships = np.zeros((K, N), np.float32)
+    oracle64.constants(ref, K)
+    soa = oracle64.transpose(ev)
+    with pkg.Engine(ev, K) as eng:
+        eng.set_option("path", path_id(pkg, path))
+        eng.seed(K)                       # establishes the global-mean shift
+        eng.set_clusters(K, ref)
+        eng.estep(K)
+        eng.mstep(K)
+        eng.constants(K)
+        got = eng.get_clusters(K)
+    oracle64.estep(soa, ref, K)
+    oracle64.mstep(soa, ref, K)
+    oracle64.constants(ref, K)
+    assert_params_close(got, ref, K)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_seed_parity(loaded, oracle64, path):
+    pkg = loaded
+    ev = pkg.synth.make_blobs(10_000, 4, 8)
+    K = 8
+    ref = pkg.Clusters(K, 4, ev.shape[0])
+    oracle64.seed(ev, K, ref)
+    with pkg.Engine(ev, K) as eng:
+        eng.set_option("path", path_id(pkg, path))
+        got = eng.seed(K)
+    np.testing.assert_array_equal(got.means, ref.means)
+    np.testing.assert_array_equal(got.N, ref.N)
+    np.testing.assert_allclose(got.avgvar, ref.avgvar, rtol=1e-5)
+    assert_params_close(got, ref, K)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_em_config1_100_iters(loaded, oracle64, path):
+    """BASELINE config 1: N=10k, D=4, K=8, the reference's fixed 100 iterations."""
+    pkg = loaded
+    cfg = pkg.synth.CONFIGS["c1"]
+    ev = pkg.synth.make_blobs(cfg["N"], cfg["D"], cfg["K"])
+    K = cfg["K"]
+    ref = pkg.Clusters(K, cfg["D"], cfg["N"])
+    oracle64.seed(ev, K, ref)
+    ll_ref, it_ref = oracle64.em(oracle64.transpose(ev), ref, K, 100, 100)
+    with pkg.Engine(ev, K) as eng:
+        eng.set_option("path", path_id(pkg, path))
+        eng.seed(K)
+        ll, it = eng.em(K, 100, 100)
+        got = eng.get_clusters(K, with_memberships=True)
+    assert it == it_ref == 100
+    assert abs(ll - ll_ref) <= 1e-5 * abs(ll_ref)
+    assert_params_close(got, ref, K)
+    assert_memb_close(got.memberships, ref.memberships, rtol=2e-4, atol=2e-6)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_em_config2_slice(loaded, oracle64, path):
+    """BASELINE config 2 shape (D=16, K=32) on a 100k-event slice, 10 iterations
+    (the oracle finishes in seconds); the full 1M/50-iteration run is covered by
+    the size-independent properties below."""
+    pkg = loaded
+    N, D, K = 100_000, 16, 32
+    ev = pkg.synth.make_blobs(N, D, K)
+    ref = pkg.Clusters(K, D, N)
+    oracle64.seed(ev, K, ref)
+    ll_ref, _ = oracle64.em(oracle64.transpose(ev), ref, K, 10, 10)
+    with pkg.Engine(ev, K) as eng:
+        eng.set_option("path", path_id(pkg, path))
+        eng.seed(K)
+        ll, it = eng.em(K, 10, 10)
+        got = eng.get_clusters(K, with_memberships=True)
+    assert it == 10
+    assert abs(ll - ll_ref) <= 1e-5 * abs(ll_ref)
+    assert_params_close(got, ref, K)
+    assert_memb_close(got.memberships, ref.memberships, rtol=2e-4, atol=2e-6)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_em_convergence_rule(loaded, oracle64, path):
+    """min_iters < max_iters: the epsilon test of gaussian.cu:532 decides."""
+    pkg = loaded
+    ev = pkg.synth.make_blobs(6_000, 3, 3, seed=4)
+    K = 3
+    ref = pkg.Clusters(K, 3, ev.shape[0])
+    oracle64.seed(ev, K, ref)
+    ll_ref, it_ref = oracle64.em(oracle64.transpose(ev), ref, K, 2, 60)
+    with pkg.Engine(ev, K) as eng:
+        eng.set_option("path", path_id(pkg, path))
+        eng.seed(K)
+        ll, it = eng.em(K, 2, 60)
+    assert 2 <= it_ref < 60
+    assert it == it_ref
+    assert abs(ll - ll_ref) <= 1e-5 * abs(ll_ref)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_fit_order_reduction(loaded, oracle64, path):
+    """gmm_fit: final cluster count integer-exact, best configuration equal."""
+    pkg = loaded
+    ev = pkg.synth.make_blobs(8_000, 4, 4, seed=12)
+    K0 = 8
+    c, s = pkg.Clusters(K0, 4, ev.shape[0]), pkg.Clusters(K0, 4, ev.shape[0])
+    ideal_ref, mr_ref = oracle64.fit(ev, K0, 0, 20, 20, c, s)
+    with pkg.Engine(ev, K0) as eng:
+        eng.set_option("path", path_id(pkg, path))
+        ideal, mr, saved = eng.fit(K0, 0, 20, 20, with_memberships=True)
+    assert ideal == ideal_ref
+    assert abs(mr - mr_ref) <= 1e-5 * abs(mr_ref)
+    assert_params_close(saved, s, ideal, rtol=5e-4)
+    assert_memb_close(saved.memberships[:ideal], s.memberships[:ideal], rtol=1e-3, atol=1e-5)
+    # explicit target
+    ideal_ref3, _ = oracle64.fit(ev, K0, 3, 20, 20, c, s)
+    with pkg.Engine(ev, K0) as eng:
+        eng.set_option("path", path_id(pkg, path))
+        ideal3, _, saved3 = eng.fit(K0, 3, 20, 20)
+    assert ideal3 == ideal_ref3 == 3
+    assert_params_close(saved3, s, 3, rtol=5e-4)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_full_size_properties_config2(loaded, path):
+    """Config 2 at full size (N=1M, D=16, K=32): size-independent properties —
+    responsibilities sum to 1, sum_k N_k = N, covariances symmetric positive
+    definite, log-likelihood non-decreasing (up to the regulariser), rerun
+    bit-stable in the parameters to 1e-6."""
+    pkg = loaded
+    cfg = pkg.synth.CONFIGS["c2"]
+    ev = pkg.synth.make_blobs(cfg["N"], cfg["D"], cfg["K"])
+    K, N = cfg["K"], cfg["N"]
+    with pkg.Engine(ev, K) as eng:
+        eng.set_option("path", path_id(pkg, path))
+        eng.seed(K)
+        lls = []
+        for i in range(6):
+            ll, _ = eng.em(K, 1, 1) if i else (eng.estep(K), 0)
+            lls.append(ll)
+        got = eng.get_clusters(K, with_memberships=True)
+    assert all(b >= a - 1e-5 * abs(a) for a, b in zip(lls, lls[1:])), lls
+    np.testing.assert_allclose(got.memberships.sum(0), 1.0, atol=1e-5)
+    assert abs(float(got.N.astype(np.float64).sum()) - N) < 1e-4 * N
+    for k in range(K):
+        np.testing.assert_array_equal(got.R[k], got.R[k].T)
+        assert np.all(np.linalg.eigvalsh(got.R[k].astype(np.float64)) > 0)
+    np.testing.assert_allclose(got.pi.sum(), 1.0, rtol=1e-5)
+
+
+def test_reference_binary_matches_oracle_and_engine(loaded, oracle64, tmp_path):
+    """The UNMODIFIED reference program (oracle/_ref/gaussianMPI_ref), run here on
+    the GPU, against the oracle and the engine: pins the oracle to the reference."""
+    pkg = loaded
+    exe = os.path.join(ROOT, "oracle", "_ref", "gaussianMPI_ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/gaussianMPI_ref not built")
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_oracle import _parse_summary
+    N, D, K, iters = 10_000, 4, 8, 20
+    ev = pkg.synth.make_blobs(N, D, K)
+    data = tmp_path / "c1.bin"
+    pkg.synth.write_bin(str(data), ev)
+    env = dict(os.environ, OMP_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="0", GMM_REF_ITERS=str(iters))
+    r = subprocess.run([exe, str(K), str(data), str(tmp_path / "ref"), str(K)], capture_output=True, text=True,
+                       env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    golden = _parse_summary(str(tmp_path / "ref.summary"))
+    assert len(golden) == K
+    rows = [l.rstrip("\n").split("\t") for l in open(tmp_path / "ref.results")]
+    memb_ref = np.array([[float(v) for v in r_[1].split(",")] for r_ in rows[:2000]])
+    cl = pkg.Clusters(K, D, N)
+    oracle64.seed(ev, K, cl)
+    oracle64.em(oracle64.transpose(ev), cl, K, iters, iters)
+    with pkg.Engine(ev, K) as eng:
+        eng.seed(K)
+        eng.em(K, iters, iters)
+        got = eng.get_clusters(K, with_memberships=True)
+    for who, c in (("oracle", cl), ("engine", got)):
+        for k in range(K):
+            g = golden[k]
+            assert abs(c.pi[k] - g["pi"]) < 2e-5, who
+            np.testing.assert_allclose(c.means[k], g["means"], atol=2e-3, err_msg=who)
+            np.testing.assert_allclose(c.R[k], np.array(g["R"]), atol=2e-3, err_msg=who)
+        np.testing.assert_allclose(c.memberships[:, :2000].T, memb_ref, atol=2e-4, err_msg=who)
+
+
+def test_cli_end_to_end(loaded, oracle64, tmp_path):
+    pkg = loaded
+    exe = os.path.join(ROOT, "cuda-gmm-mpi_b200", "gaussianMPI_b200")
+    N, D, K0 = 5_000, 3, 5
+    ev = pkg.synth.make_blobs(N, D, 3, seed=6)
+    data = tmp_path / "d.bin"
+    pkg.synth.write_bin(str(data), ev)
+    env = dict(os.environ, GMM_ITERS="15", GMM_GPUS="1")
+    r = subprocess.run([exe, str(K0), str(data), str(tmp_path / "out"), "3"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_oracle import _parse_summary
+    got = _parse_summary(str(tmp_path / "out.summary"))
+    c, s = pkg.Clusters(K0, D, N), pkg.Clusters(K0, D, N)
+    ideal = oracle64.fit(ev, K0, 3, 15, 15, c, s)[0]
+    assert ideal == 3 == len(got)
+    for k in range(3):
+        np.testing.assert_allclose(got[k]["means"], s.means[k], atol=2e-3)
+        np.testing.assert_allclose(np.array(got[k]["R"]), s.R[k], atol=2e-3)
+    rows = open(tmp_path / "out.results").read().splitlines()
+    assert len(rows) == N
+    m = np.array([float(v) for v in rows[17].split("\t")[1].split(",")])
+    np.testing.assert_allclose(m, s.memberships[:3, 17], atol=2e-4)
+
+
+@pytest.mark.skipif(gpu_count() < 2, reason="needs >= 2 GPUs")
+def test_cli_two_gpus_equals_one(loaded, tmp_path):
+    """Sharded run == single-GPU run (one NCCL all-reduce of the packed statistics)."""
+    pkg = loaded
+    exe = os.path.join(ROOT, "cuda-gmm-mpi_b200", "gaussianMPI_b200")
+    ev = pkg.synth.make_blobs(20_001, 4, 4, seed=2)
+    data = tmp_path / "d.bin"
+    pkg.synth.write_bin(str(data), ev)
+    outs = {}
+    for g in (1, 2):
+        env = dict(os.environ, GMM_ITERS="10", GMM_GPUS=str(g))
+        r = subprocess.run([exe, "4", str(data), str(tmp_path / f"o{g}"), "4"], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs[g] = open(tmp_path / f"o{g}.summary").read()
+    assert outs[1] == outs[2]
