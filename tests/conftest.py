@@ -68,6 +68,18 @@ def random_spd_params(pkg, K, D, rng, spread=4.0):
     return cl
 
 
+def fitted_params(pkg, oracle, ev, K, iters=2):
+    """Realistic parameters: the oracle's seeding followed by `iters` EM iterations
+    (so that every event has at least one cluster at a moderate Mahalanobis distance,
+    as in any real EM state)."""
+    N, D = ev.shape
+    cl = pkg.Clusters(K, D, N)
+    oracle.seed(ev, K, cl)
+    if iters:
+        oracle.em(oracle.transpose(ev), cl, K, iters, iters)
+    return cl
+
+
 def assert_params_close(got, ref, K, rtol=1e-4):
     """The parity bar of BASELINE.json: 1e-4 relative on means / covariances
     (absolute floor scaled to each cluster's largest covariance entry)."""
