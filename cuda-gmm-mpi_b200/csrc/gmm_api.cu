@@ -89,6 +89,7 @@ struct gmm_ctx {
     float* d_x_soa = nullptr;    // [D][n]  transpose for the SIMT kernels
     // responsibilities, cluster-major [Kmax][n]
     float* d_memb = nullptr;
+    size_t memb_pitch = 0;           // row pitch in floats (multiple of 32: TMA-aligned rows)
     float* d_memb_saved = nullptr;   // best configuration during gmm_fit
     // parameters
     float* d_epack = nullptr;    // SIMT E-step parameters [Kmax][epack_stride]
@@ -98,6 +99,8 @@ struct gmm_ctx {
     double* d_shift = nullptr;   // [32]
     double shift[GMM_MAX_DIMENSIONS] = {0};
     bool have_shift = false;
+    double scale[GMM_MAX_DIMENSIONS] = {0};   // global per-dimension standard deviation
+    double sum_x[GMM_MAX_DIMENSIONS] = {0}, sum_x2[GMM_MAX_DIMENSIONS] = {0};
     // host copy of the current parameters (all arrays sized for Kmax)
     std::vector<float> hN, hpi, hconst, havgvar, hmeans, hR, hRinv;
     clusters_t host{};
@@ -154,13 +157,11 @@ static void copy_params(clusters_t* dst, const clusters_t* src, int K, int D) {
     std::memcpy(dst->Rinv, src->Rinv, sizeof(float) * (size_t)K * D * D);
 }
 
-static bool use_tensor_path(const gmm_ctx* c, int K) {
-    if (c->path == GMM_PATH_SIMT) return false;
-    return tc_supported(c->D, K);
-}
-// GMM_PATH_TENSOR never degrades silently.
+static bool use_tensor_estep(const gmm_ctx* c, int K) { return c->path != GMM_PATH_SIMT && c->n > 0 && tc_estep_supported(c->D, K); }
+static bool use_tensor_mstep(const gmm_ctx* c, int K) { return c->path != GMM_PATH_SIMT && c->n > 0 && tc_mstep_supported(c->D, K); }
+// GMM_PATH_TENSOR never degrades silently: the M-step (the covariance contraction) must be covered.
 static int check_path(const gmm_ctx* c, int K) {
-    if (c->path == GMM_PATH_TENSOR && !tc_supported(c->D, K))
+    if (c->path == GMM_PATH_TENSOR && !tc_mstep_supported(c->D, K))
         return fail(GMM_ERR_ARG, "GMM_PATH_TENSOR requested but the tcgen05 kernels do not cover this (D, K)");
     return GMM_OK;
 }
@@ -171,12 +172,10 @@ static int check_path(const gmm_ctx* c, int K) {
 static int upload_params(gmm_ctx* c, int K) {
     if (int rc = check_path(c, K)) return rc;
     auto t0 = std::chrono::steady_clock::now();
-    if (use_tensor_path(c, K)) {
+    if (use_tensor_estep(c, K)) {
         int rc = tc_upload_params(c->tc, &c->host, K, c->stream);
         if (rc) return rc;
-    }
-    if (!use_tensor_path(c, K) || c->path == GMM_PATH_AUTO) {
-        // the SIMT pack is tiny; AUTO keeps it current so gmm_estep can always fall back to a supported kernel
+    } else {
         build_epack(K, c->D, &c->host, c->h_epack);
         CUDA_TRY(cudaMemcpyAsync(c->d_epack, c->h_epack, sizeof(float) * (size_t)K * epack_stride(c->D),
                                  cudaMemcpyHostToDevice, c->stream));
@@ -190,7 +189,7 @@ static int upload_params(gmm_ctx* c, int K) {
 template <int D>
 static void launch_estep_simt_d(gmm_ctx* c, int K) {
     const int blocks = (c->n + kEstepThreads - 1) / kEstepThreads;
-    estep_simt_kernel<D><<<blocks, kEstepThreads, 0, c->stream>>>(c->d_x_soa, c->n, K, c->d_epack, c->d_memb,
+    estep_simt_kernel<D><<<blocks, kEstepThreads, 0, c->stream>>>(c->d_x_soa, c->n, K, c->d_epack, c->d_memb, c->memb_pitch,
                                                                  c->d_stats + (size_t)K * c->F);
 }
 static int launch_estep_simt(gmm_ctx* c, int K) {
@@ -224,7 +223,7 @@ static int launch_mstep_simt_t(gmm_ctx* c, int K) {
     if (per < kMstepTE) per = kMstepTE;
     gx = (c->n + per - 1) / per;
     dim3 grid(gx, (K + KT - 1) / KT);
-    mstep_simt_kernel<JMAX, CPT><<<grid, kMstepThreads, smem, c->stream>>>(c->d_x_soa, c->n, c->D, K, c->d_memb,
+    mstep_simt_kernel<JMAX, CPT><<<grid, kMstepThreads, smem, c->stream>>>(c->d_x_soa, c->n, c->D, K, c->d_memb, c->memb_pitch,
                                                                            c->d_shift, c->d_stats, per);
     CUDA_TRY(cudaGetLastError());
     return GMM_OK;
@@ -260,8 +259,8 @@ static int zero_stats(gmm_ctx* c, int K) {
 // log-likelihood added to stats[K*F].
 static int run_estep(gmm_ctx* c, int K) {
     timer_begin(c, c->t_estep);
-    int rc = use_tensor_path(c, K) ? tc_launch_estep(c->tc, K, c->d_memb, c->d_stats + (size_t)K * c->F, c->stream)
-                                   : launch_estep_simt(c, K);
+    int rc = use_tensor_estep(c, K) ? tc_launch_estep(c->tc, K, c->d_stats + (size_t)K * c->F, c->stream)
+                                    : launch_estep_simt(c, K);
     timer_end(c, c->t_estep);
     c->memb_valid = (rc == GMM_OK);
     return rc;
@@ -270,8 +269,8 @@ static int run_estep(gmm_ctx* c, int K) {
 // M-step accumulation of the local statistics into stats[0 .. K*F).
 static int run_mstep_accumulate(gmm_ctx* c, int K) {
     timer_begin(c, c->t_mstep);
-    int rc = use_tensor_path(c, K) ? tc_launch_mstep(c->tc, K, c->d_memb, c->d_stats, c->stream)
-                                   : launch_mstep_simt(c, K);
+    int rc = use_tensor_mstep(c, K) ? tc_launch_mstep(c->tc, K, c->d_stats, c->stream)
+                                    : launch_mstep_simt(c, K);
     timer_end(c, c->t_mstep);
     return rc;
 }
@@ -297,6 +296,40 @@ static int finalize_and_upload(gmm_ctx* c, int K) {
     finalize_from_stats(c->h_stats, c->shift, K, c->D, &c->host, c->host_threads);
     c->host_const_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return upload_params(c, K);
+}
+
+// Global column moments (sum x, sum x^2 over ALL events of all ranks), computed once per
+// context.  They give (a) the seeding mean / average variance (gaussian_kernel.cu:54-102, with
+// quirk Q2 fixed: whole data set, double accumulation) and (b) the centre `shift` and per-
+// dimension `scale` about which the M-step statistics are accumulated.
+static int ensure_moments(gmm_ctx* c) {
+    if (c->have_shift) return GMM_OK;
+    const int D = c->D;
+    CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(double) * 2 * D, c->stream));
+    if (c->n > 0) {
+        dim3 grid(std::min(4 * c->num_sms, (c->n + 255) / 256), D);
+        column_moments_kernel<<<grid, 256, 0, c->stream>>>(c->d_x_soa, c->n, D, c->d_stats);
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (c->nranks > 1) {
+        ncclResult_t r = nccl().AllReduce(c->d_stats, c->d_stats, 2 * D, ncclDouble, ncclSum, c->comm, c->stream);
+        if (r != ncclSuccess) return fail(GMM_ERR_NCCL, std::string("ncclAllReduce: ") + nccl().GetErrorString(r));
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(double) * 2 * D, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int d = 0; d < D; d++) {
+        c->sum_x[d] = c->h_stats[d];
+        c->sum_x2[d] = c->h_stats[D + d];
+        const double mean = c->sum_x[d] / (double)c->n_global;
+        const double var = c->sum_x2[d] / (double)c->n_global - mean * mean;
+        c->shift[d] = mean;
+        c->scale[d] = var > 0 ? std::sqrt(var) : 1.0;
+    }
+    if (int rc = tc_set_shift_scale(c->tc, c->shift, c->scale, c->stream)) return rc;   // rounds shift to float in place
+    CUDA_TRY(cudaMemcpyAsync(c->d_shift, c->shift, sizeof(double) * D, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->have_shift = true;
+    return GMM_OK;
 }
 
 static int check_K(const gmm_ctx* c, int K, const char* who) {
@@ -353,7 +386,8 @@ int gmm_create(gmm_ctx** out, int device, int n_local, int D, int Kmax, const fl
     const size_t nmax = n_local > 0 ? (size_t)n_local : 1;
     CREATE_TRY(cudaMalloc(&c->d_x_aos, sizeof(float) * nmax * D));
     CREATE_TRY(cudaMalloc(&c->d_x_soa, sizeof(float) * nmax * D));
-    CREATE_TRY(cudaMalloc(&c->d_memb, sizeof(float) * nmax * Kmax));
+    c->memb_pitch = (nmax + 31) / 32 * 32;
+    CREATE_TRY(cudaMalloc(&c->d_memb, sizeof(float) * c->memb_pitch * Kmax));
     CREATE_TRY(cudaMalloc(&c->d_epack, sizeof(float) * (size_t)Kmax * epack_stride(D)));
     CREATE_TRY(cudaMallocHost(&c->h_epack, sizeof(float) * (size_t)Kmax * epack_stride(D)));
     CREATE_TRY(cudaMalloc(&c->d_stats, sizeof(double) * ((size_t)Kmax * c->F + 1)));
@@ -367,7 +401,7 @@ int gmm_create(gmm_ctx** out, int device, int n_local, int D, int Kmax, const fl
         CREATE_TRY(cudaGetLastError());
     }
     {
-        int rc = tc_create(&c->tc, c->d_x_aos, n_local, D, Kmax, c->num_sms, c->stream);
+        int rc = tc_create(&c->tc, c->d_x_aos, n_local, D, Kmax, c->d_memb, c->memb_pitch, c->num_sms, c->stream);
         if (rc) { gmm_destroy(c); return rc; }
     }
     CREATE_TRY(cudaStreamSynchronize(c->stream));
@@ -439,18 +473,12 @@ int gmm_set_option(gmm_ctx* c, const char* key, double value) {
 int gmm_seed(gmm_ctx* c, int K, clusters_t* host_out) {
     if (int rc = check_K(c, K, "gmm_seed")) return rc;
     CUDA_TRY(cudaSetDevice(c->device));
+    if (int rc = ensure_moments(c)) return rc;
     const int D = c->D;
-    // packed: [sum x (D) | sum x^2 (D) | seed rows (K*D)] in double, reduced over ranks.
-    const size_t len = (size_t)2 * D + (size_t)K * D;
+    // seed rows (evenly spaced events, gaussian.cu:110-120): the owning shard contributes, the others add zeros
+    const size_t len = (size_t)K * D;
     if (len > (size_t)c->Kmax * c->F + 1) return fail(GMM_ERR_STATE, "gmm_seed: stats buffer too small");
-    CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(double) * len, c->stream));
-    if (c->n > 0) {
-        dim3 grid(std::min(4 * c->num_sms, (c->n + 255) / 256), D);
-        column_moments_kernel<<<grid, 256, 0, c->stream>>>(c->d_x_soa, c->n, D, c->d_stats);
-        CUDA_TRY(cudaGetLastError());
-    }
-    // seed rows owned by this shard (evenly spaced events, gaussian.cu:110-120)
-    std::vector<double> rows((size_t)K * D, 0.0);
+    std::vector<double> rows(len, 0.0);
     std::vector<float> tmp(D);
     for (int k = 0; k < K; k++) {
         const long long g = seed_event_index(k, K, c->n_global);
@@ -461,21 +489,16 @@ int gmm_seed(gmm_ctx* c, int K, clusters_t* host_out) {
             for (int d = 0; d < D; d++) rows[(size_t)k * D + d] = tmp[d];
         }
     }
-    CUDA_TRY(cudaMemcpyAsync(c->d_stats + 2 * D, rows.data(), sizeof(double) * K * D, cudaMemcpyHostToDevice, c->stream));
     if (c->nranks > 1) {
+        CUDA_TRY(cudaMemcpyAsync(c->d_stats, rows.data(), sizeof(double) * len, cudaMemcpyHostToDevice, c->stream));
         ncclResult_t r = nccl().AllReduce(c->d_stats, c->d_stats, len, ncclDouble, ncclSum, c->comm, c->stream);
         if (r != ncclSuccess) return fail(GMM_ERR_NCCL, std::string("ncclAllReduce: ") + nccl().GetErrorString(r));
+        CUDA_TRY(cudaMemcpyAsync(rows.data(), c->d_stats, sizeof(double) * len, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
     }
-    CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(double) * len, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    std::vector<float> seed_rows((size_t)K * D);
-    for (size_t i = 0; i < seed_rows.size(); i++) seed_rows[i] = (float)c->h_stats[2 * D + i];
-    seed_from_moments(c->h_stats, c->h_stats + D, c->n_global, D, K, seed_rows.data(), &c->host);
-    // Statistics are accumulated about the global mean (DESIGN.md "shift").
-    for (int d = 0; d < D; d++) c->shift[d] = c->h_stats[d] / (double)c->n_global;
-    c->have_shift = true;
-    CUDA_TRY(cudaMemcpyAsync(c->d_shift, c->shift, sizeof(double) * D, cudaMemcpyHostToDevice, c->stream));
-    if (int rc = tc_set_shift(c->tc, c->shift, c->stream)) return rc;
+    std::vector<float> seed_rows(len);
+    for (size_t i = 0; i < len; i++) seed_rows[i] = (float)rows[i];
+    seed_from_moments(c->sum_x, c->sum_x2, c->n_global, D, K, seed_rows.data(), &c->host);
     if (int rc = upload_params(c, K)) return rc;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->memb_valid = false;
@@ -503,7 +526,8 @@ int gmm_get_clusters(gmm_ctx* c, int K, clusters_t* out, int with_memberships) {
         if (!out->memberships) return fail(GMM_ERR_ARG, "gmm_get_clusters: memberships requested but pointer is null");
         if (!c->memb_valid) return fail(GMM_ERR_STATE, "gmm_get_clusters: no E-step has run for the current parameters");
         if (c->n > 0)
-            CUDA_TRY(cudaMemcpyAsync(out->memberships, c->d_memb, sizeof(float) * (size_t)K * c->n, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaMemcpy2DAsync(out->memberships, sizeof(float) * (size_t)c->n, c->d_memb, sizeof(float) * c->memb_pitch,
+                                       sizeof(float) * (size_t)c->n, K, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
     }
     return GMM_OK;
@@ -530,11 +554,8 @@ int gmm_estep(gmm_ctx* c, int K, float* loglik_out) {
 int gmm_mstep(gmm_ctx* c, int K) {
     if (int rc = check_K(c, K, "gmm_mstep")) return rc;
     if (!c->memb_valid || K != c->cur_K) return fail(GMM_ERR_STATE, "gmm_mstep: run gmm_estep first");
-    if (!c->have_shift) {      // parameters came from gmm_set_clusters without gmm_seed: zero shift is valid, just less conditioned
-        for (int d = 0; d < c->D; d++) c->shift[d] = 0.0;
-        c->have_shift = true;
-    }
     CUDA_TRY(cudaSetDevice(c->device));
+    if (int rc = ensure_moments(c)) return rc;
     const double ll_keep = c->h_stats[(size_t)K * c->F];
     CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(double) * (size_t)K * c->F, c->stream));
     if (int rc = run_mstep_accumulate(c, K)) return rc;
@@ -589,8 +610,8 @@ static int reduce_loglik_to_host(gmm_ctx* c, int K, float* out) {
 int gmm_em_iterations(gmm_ctx* c, int K, int iters, float* loglik_out) {
     if (int rc = check_K(c, K, "gmm_em_iterations")) return rc;
     if (!c->memb_valid || K != c->cur_K) return fail(GMM_ERR_STATE, "gmm_em_iterations: run gmm_estep first");
-    if (!c->have_shift) { for (int d = 0; d < c->D; d++) c->shift[d] = 0.0; c->have_shift = true; }
     CUDA_TRY(cudaSetDevice(c->device));
+    if (int rc = ensure_moments(c)) return rc;
     for (int i = 0; i < iters; i++)
         if (int rc = em_iteration(c, K, nullptr)) return rc;
     if (int rc = reduce_loglik_to_host(c, K, loglik_out)) return rc;
@@ -607,8 +628,8 @@ int gmm_em_iterations(gmm_ctx* c, int K, int iters, float* loglik_out) {
 int gmm_em(gmm_ctx* c, int K, int min_iters, int max_iters, float epsilon, float* loglik_out, int* iters_out) {
     if (int rc = check_K(c, K, "gmm_em")) return rc;
     if (K != c->cur_K) return fail(GMM_ERR_STATE, "gmm_em: parameters for this K have not been set (gmm_seed / gmm_set_clusters)");
-    if (!c->have_shift) { for (int d = 0; d < c->D; d++) c->shift[d] = 0.0; c->have_shift = true; }
     CUDA_TRY(cudaSetDevice(c->device));
+    if (int rc = ensure_moments(c)) return rc;
     if (epsilon < 0) epsilon = em_epsilon(c->D, c->n_global);
     const size_t ll_idx = (size_t)K * c->F;
     if (int rc = zero_stats(c, K)) return rc;
@@ -669,7 +690,7 @@ int gmm_fit(gmm_ctx* c, int K0, int target_K, int min_iters, int max_iters, clus
     float min_rissanen = 0;
     int ideal = K0;
     if (saved->memberships && !c->d_memb_saved && c->n > 0)
-        CUDA_TRY(cudaMalloc(&c->d_memb_saved, sizeof(float) * (size_t)c->n * c->Kmax));
+        CUDA_TRY(cudaMalloc(&c->d_memb_saved, sizeof(float) * c->memb_pitch * c->Kmax));
     for (int K = K0; K >= stop_number;) {
         float likelihood; int iters;
         if (int rc = gmm_em(c, K, min_iters, max_iters, epsilon, &likelihood, &iters)) return rc;
@@ -680,7 +701,7 @@ int gmm_fit(gmm_ctx* c, int K0, int target_K, int min_iters, int max_iters, clus
             ideal = K;
             copy_params(saved, &c->host, K, D);
             if (saved->memberships && c->n > 0)
-                CUDA_TRY(cudaMemcpyAsync(c->d_memb_saved, c->d_memb, sizeof(float) * (size_t)K * c->n, cudaMemcpyDeviceToDevice, c->stream));
+                CUDA_TRY(cudaMemcpyAsync(c->d_memb_saved, c->d_memb, sizeof(float) * (size_t)K * c->memb_pitch, cudaMemcpyDeviceToDevice, c->stream));
         }
         if (K > stop_number) {                                            // :860-950
             K = reduce_order(&c->host, K, D, nullptr, nullptr, c->host_threads);
@@ -690,7 +711,8 @@ int gmm_fit(gmm_ctx* c, int K0, int target_K, int min_iters, int max_iters, clus
         } else break;
     }
     if (saved->memberships && c->n > 0) {
-        CUDA_TRY(cudaMemcpyAsync(saved->memberships, c->d_memb_saved, sizeof(float) * (size_t)ideal * c->n, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpy2DAsync(saved->memberships, sizeof(float) * (size_t)c->n, c->d_memb_saved, sizeof(float) * c->memb_pitch,
+                                   sizeof(float) * (size_t)c->n, ideal, cudaMemcpyDeviceToHost, c->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (ideal_K) *ideal_K = ideal;

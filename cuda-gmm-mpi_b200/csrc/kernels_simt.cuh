@@ -40,7 +40,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 template <int D>
 __global__ void __launch_bounds__(kEstepThreads)
 estep_simt_kernel(const float* __restrict__ xs, int n, int K, const float* __restrict__ epack,
-                  float* __restrict__ memb, double* __restrict__ ll_out) {
+                  float* __restrict__ memb, size_t pitch, double* __restrict__ ll_out) {
     constexpr int STRIDE = epack_stride_c(D);
     constexpr int COEF = (D + 3) & ~3;
     constexpr int NCOEF = D * (D + 1) / 2;
@@ -78,7 +78,7 @@ estep_simt_kernel(const float* __restrict__ xs, int n, int K, const float* __res
                 q = fmaf(dx[i], t, q);
             }
             const float l = fmaf(-0.5f, q, p[COEF + NCOEF]);
-            if (valid) memb[(size_t)(k0 + kk) * n + e] = l;
+            if (valid) memb[(size_t)(k0 + kk) * pitch + e] = l;
             const float m2 = fmaxf(run_max, l);
             run_sum = run_sum * expf(run_max - m2) + expf(l - m2);
             run_max = m2;
@@ -87,7 +87,7 @@ estep_simt_kernel(const float* __restrict__ xs, int n, int K, const float* __res
     const float denom = run_max + logf(run_sum);            // estep2 :490-494
     if (valid) {
         for (int k = 0; k < K; k++) {
-            float* g = memb + (size_t)k * n + e;
+            float* g = memb + (size_t)k * pitch + e;
             *g = expf(*g - denom);                          // estep2 :498-501
         }
     }
@@ -119,7 +119,7 @@ constexpr int kMstepTE = 32;
 
 template <int JMAX, int CPT>
 __global__ void __launch_bounds__(kMstepThreads, 1)
-mstep_simt_kernel(const float* __restrict__ xs, int n, int D, int K, const float* __restrict__ memb,
+mstep_simt_kernel(const float* __restrict__ xs, int n, int D, int K, const float* __restrict__ memb, size_t pitch,
                   const double* __restrict__ shift, double* __restrict__ stats, int events_per_block) {
     constexpr int FP = 16 * JMAX;          // padded feature count
     constexpr int KT = 16 * CPT;           // clusters per block
@@ -166,7 +166,7 @@ mstep_simt_kernel(const float* __restrict__ xs, int n, int D, int K, const float
             const int kk = idx / kMstepTE, t = idx % kMstepTE;
             const long long e = e0 + t;
             const int k = k0 + kk;
-            gt[t * GS + kk] = (k < K && e < eend) ? (double)memb[(size_t)k * n + e] : 0.0;
+            gt[t * GS + kk] = (k < K && e < eend) ? (double)memb[(size_t)k * pitch + e] : 0.0;
         }
         __syncthreads();
         for (int idx = tid; idx < kMstepTE * FP; idx += kMstepThreads) {      // features

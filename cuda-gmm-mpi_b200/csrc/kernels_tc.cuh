@@ -8,14 +8,20 @@ namespace gmm {
 
 struct TcState;
 
-// Shapes the tensor-core kernels cover.
-bool tc_supported(int D, int K);
+// Shapes the tensor-core kernels cover (independently for the two steps).
+bool tc_mstep_supported(int D, int K);
+bool tc_estep_supported(int D, int K);
 
-int  tc_create(TcState** out, const float* d_x_aos, int n, int D, int Kmax, int num_sms, cudaStream_t stream);
+// memb_pitch: row pitch (in floats) of the cluster-major responsibilities buffer.
+int  tc_create(TcState** out, const float* d_x_aos, int n, int D, int Kmax, float* d_memb, size_t memb_pitch,
+               int num_sms, cudaStream_t stream);
 void tc_destroy(TcState*);
-int  tc_set_shift(TcState*, const double* shift, cudaStream_t stream);
+// Centre/scale used inside the tensor kernels: z = (x - shift) * inv_scale, both rounded to
+// float; `shift` is updated in place to the float-rounded values actually used.
+int  tc_set_shift_scale(TcState*, double* shift, const double* scale, cudaStream_t stream);
 int  tc_upload_params(TcState*, const clusters_t* host, int K, cudaStream_t stream);
-int  tc_launch_estep(TcState*, int K, float* d_memb, double* d_ll, cudaStream_t stream);
-int  tc_launch_mstep(TcState*, int K, const float* d_memb, double* d_stats, cudaStream_t stream);
+int  tc_launch_estep(TcState*, int K, double* d_ll, cudaStream_t stream);
+// Accumulates sum_n g[k][n] * phi_f(x_n - shift) into d_stats[k*F + f] (double, original units).
+int  tc_launch_mstep(TcState*, int K, double* d_stats, cudaStream_t stream);
 
 }  // namespace gmm

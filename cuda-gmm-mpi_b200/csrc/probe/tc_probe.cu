@@ -1,0 +1,331 @@
+// tc_probe.cu — development probe for the tcgen05 building blocks used by
+// kernels_tc.cu.  Run on a B200:  ./tc_probe  (prints PASS/FAIL lines + timings)
+//   T1  operand layouts: MN-major A / K-major A with SWIZZLE_NONE descriptors,
+//       K-major B, M=128, checks D = A * B^T exactly (small integers).
+//   T2  rounding behaviour of the FP32 accumulation in TMEM (RN vs truncation).
+//   T3  MMA issue throughput for the shapes of the M-step (N=64) and E-step (N=192).
+//   T4  tcgen05.ld throughput (TMEM -> registers).
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../tc_ptx.cuh"
+
+using namespace gmm::ptx;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+struct ProbeArgs {
+    const uint8_t* a_img; const uint8_t* b_img;   // smem images (bytes)
+    int a_bytes, b_bytes;
+    int a_lbo, a_sbo, b_lbo, b_sbo;               // descriptor byte offsets
+    int a_kstep_bytes, b_kstep_bytes;             // start-address advance per K=16 step
+    int a_mn_major;
+    int N, ksteps, repeats, ndst;
+    float* d_out;                                 // [128][N]
+    long long* cycles;                            // [0] = mma cycles
+};
+
+__global__ void __launch_bounds__(128, 1) probe_mma_kernel(ProbeArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t* sa = smem;
+    uint8_t* sb = smem + ((p.a_bytes + 1023) & ~1023);
+    for (int i = threadIdx.x * 16; i < p.a_bytes; i += blockDim.x * 16) *(uint4*)(sa + i) = *(const uint4*)(p.a_img + i);
+    for (int i = threadIdx.x * 16; i < p.b_bytes; i += blockDim.x * 16) *(uint4*)(sb + i) = *(const uint4*)(p.b_img + i);
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (threadIdx.x < 32) tmem_alloc<512>(&tmem_base_s);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_f16(128, p.N, p.a_mn_major != 0, false);
+        long long t0 = clock64();
+        if (p.ksteps == 4 && p.repeats > 1) {
+            // lean issue loop: descriptors precomputed, fully unrolled body (throughput measurement)
+            uint64_t ad[4], bd[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                ad[k] = make_smem_desc(smem_u32(sa) + k * p.a_kstep_bytes, p.a_lbo, p.a_sbo);
+                bd[k] = make_smem_desc(smem_u32(sb) + k * p.b_kstep_bytes, p.b_lbo, p.b_sbo);
+            }
+            const uint32_t d0 = tmem, d1 = tmem + (p.ndst > 1 ? p.N : 0), d2 = tmem + (p.ndst > 2 ? 2 * p.N : 0),
+                           d3 = tmem + (p.ndst > 3 ? 3 * p.N : (p.ndst > 1 ? p.N : 0));
+            mma_f16_ss(d0, ad[0], bd[0], idesc, false);
+            mma_f16_ss(d1, ad[1], bd[1], idesc, p.ndst <= 1);
+            mma_f16_ss(d2, ad[2], bd[2], idesc, p.ndst <= 2);
+            mma_f16_ss(d3, ad[3], bd[3], idesc, p.ndst <= 3);
+#pragma unroll 1
+            for (int r = 1; r < p.repeats; r++) {
+                mma_f16_ss(d0, ad[0], bd[0], idesc, true);
+                mma_f16_ss(d1, ad[1], bd[1], idesc, true);
+                mma_f16_ss(d2, ad[2], bd[2], idesc, true);
+                mma_f16_ss(d3, ad[3], bd[3], idesc, true);
+            }
+        } else {
+            for (int r = 0; r < p.repeats; r++)
+                for (int k = 0; k < p.ksteps; k++) {
+                    uint64_t ad = make_smem_desc(smem_u32(sa) + k * p.a_kstep_bytes, p.a_lbo, p.a_sbo);
+                    uint64_t bd = make_smem_desc(smem_u32(sb) + k * p.b_kstep_bytes, p.b_lbo, p.b_sbo);
+                    mma_f16_ss(tmem, ad, bd, idesc, (r | k) != 0);
+                }
+        }
+        mma_commit(&bar);
+        mbar_wait(&bar, 0);
+        long long t1 = clock64();
+        if (p.cycles) p.cycles[0] = t1 - t0;
+    }
+    __syncthreads();
+    tc_fence_after();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c0 = 0; c0 < p.N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
+        tmem_ld_wait();
+        for (int j = 0; j < 32 && c0 + j < p.N; j++) p.d_out[(size_t)(warp * 32 + lane) * p.N + c0 + j] = __uint_as_float(r[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc<512>(tmem);
+}
+
+// T4: TMEM load throughput
+__global__ void __launch_bounds__(128, 1) probe_ld_kernel(int iters, long long* cycles, float* sink) {
+    __shared__ uint32_t tmem_base_s;
+    if (threadIdx.x < 32) tmem_alloc<512>(&tmem_base_s);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const int warp = threadIdx.x >> 5;
+    float acc = 0;
+    __syncthreads();
+    long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int c0 = 0; c0 < 192; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j++) acc = fmaf(__uint_as_float(r[j]), __uint_as_float(r[j]), acc);
+        }
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[0] = t1 - t0;
+    if (acc == 123.456f) sink[0] = acc;
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc<512>(tmem);
+}
+
+// T4b: TMEM load throughput, better overlapped.  mode 0 loads only; 1 = + FFMA squares (4 chains); 2 = + fma.rn.f32x2 squares
+__global__ void __launch_bounds__(256, 1) probe_ld2_kernel(int iters, int mode, long long* cycles, float* sink) {
+    __shared__ uint32_t tmem_base_s;
+    if (threadIdx.x < 32) tmem_alloc<512>(&tmem_base_s);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane_base = ((uint32_t)((warp & 3) * 32) << 16);
+    float a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    unsigned long long p0 = 0, p1 = 0;
+    uint32_t x = 0;
+    __syncthreads();
+    long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int c0 = 0; c0 < 192; c0 += 64) {
+            uint32_t r[32], q[32];
+            tmem_ld_32x32(tmem + lane_base + c0, r);
+            tmem_ld_32x32(tmem + lane_base + c0 + 32, q);
+            tmem_ld_wait();
+            if (mode == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) x ^= r[j] ^ q[j];
+            } else if (mode == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    a0 = fmaf(__uint_as_float(r[j]), __uint_as_float(r[j]), a0);
+                    a1 = fmaf(__uint_as_float(r[j + 1]), __uint_as_float(r[j + 1]), a1);
+                    a2 = fmaf(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 2]), a2);
+                    a3 = fmaf(__uint_as_float(r[j + 3]), __uint_as_float(r[j + 3]), a3);
+                    a0 = fmaf(__uint_as_float(q[j]), __uint_as_float(q[j]), a0);
+                    a1 = fmaf(__uint_as_float(q[j + 1]), __uint_as_float(q[j + 1]), a1);
+                    a2 = fmaf(__uint_as_float(q[j + 2]), __uint_as_float(q[j + 2]), a2);
+                    a3 = fmaf(__uint_as_float(q[j + 3]), __uint_as_float(q[j + 3]), a3);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    unsigned long long v0 = ((unsigned long long)r[j + 1] << 32) | r[j];
+                    unsigned long long v1 = ((unsigned long long)r[j + 3] << 32) | r[j + 2];
+                    unsigned long long w0 = ((unsigned long long)q[j + 1] << 32) | q[j];
+                    unsigned long long w1 = ((unsigned long long)q[j + 3] << 32) | q[j + 2];
+                    asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(p0) : "l"(v0));
+                    asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(p1) : "l"(v1));
+                    asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(p0) : "l"(w0));
+                    asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(p1) : "l"(w1));
+                }
+            }
+        }
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[0] = t1 - t0;
+    if (a0 + a1 + a2 + a3 == 123.456f || x == 0x12345678u || p0 + p1 == 0x1234ull) sink[0] = a0;
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc<512>(tmem);
+}
+
+// ---- host-side layout builders (the formulas of tc_ptx.cuh) -----------------
+static void put_h(std::vector<uint8_t>& img, size_t off, float v) {
+    __half h = __float2half_rn(v);
+    memcpy(&img[off], &h, 2);
+}
+// K-major, no swizzle: [kchunk][row][16B]; LBO = rows*16, SBO = 128
+static std::vector<uint8_t> build_kmajor(const std::vector<float>& m, int rows, int K, int& lbo, int& sbo) {
+    lbo = rows * 16; sbo = 128;
+    std::vector<uint8_t> img((size_t)rows * K * 2, 0);
+    for (int r = 0; r < rows; r++)
+        for (int k = 0; k < K; k++) {
+            size_t off = (size_t)(r / 8) * sbo + (size_t)((k * 2) / 16) * lbo + (r % 8) * 16 + (k * 2) % 16;
+            put_h(img, off, m[(size_t)r * K + k]);
+        }
+    return img;
+}
+// MN-major, no swizzle: [mn-chunk of 8][k][16B]; LBO = 128 (next 8 k's), SBO = K*16 (next 8 mn)
+static std::vector<uint8_t> build_mnmajor(const std::vector<float>& m, int rows, int K, int& lbo, int& sbo) {
+    lbo = 128; sbo = K * 16;
+    std::vector<uint8_t> img((size_t)rows * K * 2, 0);
+    for (int r = 0; r < rows; r++)
+        for (int k = 0; k < K; k++) {
+            size_t off = (size_t)((r * 2) / 16) * sbo + (size_t)(k / 8) * lbo + (k % 8) * 16 + (r * 2) % 16;
+            put_h(img, off, m[(size_t)r * K + k]);
+        }
+    return img;
+}
+
+struct Result { std::vector<float> D; long long cycles; };
+
+static Result run_mma(const std::vector<float>& A, const std::vector<float>& B, int N, int K, bool a_mn, int repeats, int ndst = 1) {
+    ProbeArgs p{};
+    int albo, asbo, blbo, bsbo;
+    std::vector<uint8_t> ai = a_mn ? build_mnmajor(A, 128, K, albo, asbo) : build_kmajor(A, 128, K, albo, asbo);
+    std::vector<uint8_t> bi = build_kmajor(B, N, K, blbo, bsbo);
+    uint8_t *da, *db; float* dout; long long* dcyc;
+    CK(cudaMalloc(&da, ai.size())); CK(cudaMalloc(&db, bi.size()));
+    CK(cudaMalloc(&dout, sizeof(float) * 128 * N)); CK(cudaMalloc(&dcyc, 8));
+    CK(cudaMemcpy(da, ai.data(), ai.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(db, bi.data(), bi.size(), cudaMemcpyHostToDevice));
+    p.a_img = da; p.b_img = db; p.a_bytes = (int)ai.size(); p.b_bytes = (int)bi.size();
+    p.a_lbo = albo; p.a_sbo = asbo; p.b_lbo = blbo; p.b_sbo = bsbo;
+    p.a_kstep_bytes = 2 * albo;       // one K=16 step = two 16-byte K chunks (K-major) or two 8-k groups (MN-major)
+    p.b_kstep_bytes = 2 * blbo;
+    p.a_mn_major = a_mn; p.N = N; p.ksteps = K / 16; p.repeats = repeats; p.ndst = ndst; p.d_out = dout; p.cycles = dcyc;
+    size_t smem = ((ai.size() + 1023) & ~1023) + bi.size() + 1024;
+    CK(cudaFuncSetAttribute(probe_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    probe_mma_kernel<<<1, 128, smem>>>(p);
+    CK(cudaDeviceSynchronize());
+    Result r; r.D.resize((size_t)128 * N);
+    CK(cudaMemcpy(r.D.data(), dout, sizeof(float) * 128 * N, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&r.cycles, dcyc, 8, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dout); cudaFree(dcyc);
+    return r;
+}
+
+static float h2f(float v) { return __half2float(__float2half_rn(v)); }
+
+int main() {
+    srand(1234);
+    // ---- T1: layouts ----
+    for (int a_mn = 0; a_mn <= 1; a_mn++)
+        for (int N : {64, 192}) {
+            const int K = 80 - (a_mn ? 16 : 0);          // 5 / 4 k-steps
+            std::vector<float> A((size_t)128 * K), B((size_t)N * K);
+            for (auto& v : A) v = (float)(rand() % 9 - 4);
+            for (auto& v : B) v = (float)(rand() % 7 - 3);
+            Result r = run_mma(A, B, N, K, a_mn, 1);
+            double maxerr = 0;
+            for (int m = 0; m < 128; m++)
+                for (int n = 0; n < N; n++) {
+                    double ref = 0;
+                    for (int k = 0; k < K; k++) ref += (double)A[(size_t)m * K + k] * B[(size_t)n * K + k];
+                    maxerr = fmax(maxerr, fabs(ref - r.D[(size_t)m * N + n]));
+                }
+            printf("T1 layout A=%s-major N=%d K=%d : max|err| = %g  %s\n", a_mn ? "MN" : "K", N, K, maxerr, maxerr == 0 ? "PASS" : "FAIL");
+        }
+    // ---- T2: accumulation rounding ----
+    {
+        const int N = 64, K = 16;
+        std::vector<float> A((size_t)128 * K), B((size_t)N * K);
+        for (auto& v : A) v = h2f(0.5f + (rand() % 1000) / 1000.0f);
+        for (auto& v : B) v = h2f(0.5f + (rand() % 1000) / 1000.0f);
+        for (int repeats : {1, 64, 1024, 16384}) {
+            Result r = run_mma(A, B, N, K, false, repeats);
+            double bias = 0, rms = 0;
+            for (int m = 0; m < 128; m++)
+                for (int n = 0; n < N; n++) {
+                    double p = 0;
+                    for (int k = 0; k < K; k++) p += (double)A[(size_t)m * K + k] * B[(size_t)n * K + k];
+                    double ref = p * repeats;
+                    double rel = (r.D[(size_t)m * N + n] - ref) / ref;
+                    bias += rel; rms += rel * rel;
+                }
+            bias /= 128.0 * N; rms = sqrt(rms / (128.0 * N));
+            printf("T2 accumulate %6d k-steps: mean rel err = %+.3e  rms = %.3e  (2^-24 = 5.96e-08; truncation predicts mean ~ -steps*3e-8)\n",
+                   repeats, bias, rms);
+        }
+    }
+    // ---- T3: MMA throughput (single CTA) ----
+    for (int N : {64, 192, 256}) {
+        const int K = 64;
+        std::vector<float> A((size_t)128 * K, 1.0f), B((size_t)N * K, 1.0f);
+        Result r = run_mma(A, B, N, K, false, 2048);
+        double per = (double)r.cycles / (2048.0 * (K / 16));
+        printf("T3 M=128 N=%d K=16 fp16: %.1f cycles per MMA (floor 128*N/256 = %d)\n", N, per, 128 * N / 256);
+    }
+    for (int N : {64, 128})
+        for (int ndst : {1, 2, 3, 4}) {
+            if (N * ndst > 512) continue;
+            const int K = 64;
+            std::vector<float> A((size_t)128 * K, 1.0f), B((size_t)N * K, 1.0f);
+            Result r = run_mma(A, B, N, K, false, 2048, ndst);
+            printf("T3b M=128 N=%d round-robin over %d accumulators: %.1f cycles per MMA\n", N, ndst, (double)r.cycles / (2048.0 * (K / 16)));
+        }
+    {
+        long long* dcyc; float* sink;
+        CK(cudaMalloc(&dcyc, 8)); CK(cudaMalloc(&sink, 4));
+        for (int mode = 0; mode < 3; mode++)
+            for (int warps : {4, 8}) {
+                probe_ld2_kernel<<<1, warps * 32>>>(2000, mode, dcyc, sink);
+                CK(cudaDeviceSynchronize());
+                long long c; CK(cudaMemcpy(&c, dcyc, 8, cudaMemcpyDeviceToHost));
+                double bytes = 2000.0 * 128 * 192 * 4 * (warps / 4);
+                printf("T4b mode %d (%s) %d warps: %.1f cycles per 128x192 tile per warpgroup, %.1f B/cycle/SM\n", mode,
+                       mode == 0 ? "loads only" : mode == 1 ? "loads + 4-way FFMA squares" : "loads + f32x2 squares", warps,
+                       c / 2000.0, bytes / c);
+            }
+    }
+    // ---- T4: tcgen05.ld throughput ----
+    {
+        long long* dcyc; float* sink;
+        CK(cudaMalloc(&dcyc, 8)); CK(cudaMalloc(&sink, 4));
+        probe_ld_kernel<<<1, 128>>>(2000, dcyc, sink);
+        CK(cudaDeviceSynchronize());
+        long long c; CK(cudaMemcpy(&c, dcyc, 8, cudaMemcpyDeviceToHost));
+        double bytes = 2000.0 * 128 * 192 * 4;
+        printf("T4 tcgen05.ld 32x32b.x32 + 32 FFMA per load, 4 warps: %.1f cycles per 128x192 tile, %.1f B/cycle/SM\n", c / 2000.0, bytes / c);
+    }
+    printf("probe done\n");
+    return 0;
+}

@@ -95,6 +95,28 @@ def test_mstep_constants_parity(loaded, oracle64, path, N, D, K):
     assert_params_close(got, ref, K)
 
 
+@pytest.mark.parametrize("N,D,K", [(200_000, 24, 64), (150_001, 16, 32), (100_000, 4, 8), (70_000, 24, 100)])
+def test_mstep_tensor_path_large(loaded, oracle64, N, D, K):
+    """The tcgen05 M-step (GMM_PATH_TENSOR) on enough events to exercise several TMEM
+    flush chunks per CTA, against the oracle M-step on the same responsibilities."""
+    pkg = loaded
+    ev = pkg.synth.make_blobs(N, D, min(K, 16), seed=300 + D)
+    ref = fitted_params(pkg, oracle64, ev, K, iters=1)
+    soa = oracle64.transpose(ev)
+    with pkg.Engine(ev, K) as eng:
+        eng.set_option("path", pkg.PATH_TENSOR)
+        eng.seed(K)
+        eng.set_clusters(K, ref)
+        eng.estep(K)
+        eng.mstep(K)
+        eng.constants(K)
+        got = eng.get_clusters(K)
+    oracle64.estep(soa, ref, K)
+    oracle64.mstep(soa, ref, K)
+    oracle64.constants(ref, K)
+    assert_params_close(got, ref, K)
+
+
 @pytest.mark.parametrize("path", PATHS)
 def test_seed_parity(loaded, oracle64, path):
     pkg = loaded
