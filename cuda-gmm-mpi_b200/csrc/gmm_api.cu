@@ -118,6 +118,7 @@ struct gmm_ctx {
     double host_const_ms = 0, memcpy_ms = 0;
     long long iterations = 0;
     TcState* tc = nullptr;       // tensor-core path state (kernels_tc.cuh)
+    bool estep_tensor_ready = false;   // the tensor E-step operand of the current parameters is uploaded
 };
 
 namespace gmm {
@@ -166,16 +167,24 @@ static int check_path(const gmm_ctx* c, int K) {
     return GMM_OK;
 }
 
+static int ensure_moments(gmm_ctx* c);
+
 // Upload the current host parameters in the form the E-step kernels consume
 // (gaussian.cu:446-452 / 935-941 upload the seven raw arrays; here the E-step
 // operand is pre-packed on the host once per iteration).
 static int upload_params(gmm_ctx* c, int K) {
     if (int rc = check_path(c, K)) return rc;
     auto t0 = std::chrono::steady_clock::now();
+    c->estep_tensor_ready = false;
     if (use_tensor_estep(c, K)) {
-        int rc = tc_upload_params(c->tc, &c->host, K, c->stream);
-        if (rc) return rc;
-    } else {
+        if (int rc = ensure_moments(c)) return rc;
+        const int rc = tc_upload_params(c->tc, &c->host, K, c->stream);
+        if (rc == GMM_OK) c->estep_tensor_ready = true;
+        else if (rc != GMM_ERR_STATE || c->path == GMM_PATH_TENSOR) return rc;
+        // GMM_ERR_STATE under GMM_PATH_AUTO: a cluster whose inverse covariance is not positive definite
+        // (or does not fit FP16) — this parameter set is evaluated by the FP32 SIMT kernel instead.
+    }
+    if (!c->estep_tensor_ready) {
         build_epack(K, c->D, &c->host, c->h_epack);
         CUDA_TRY(cudaMemcpyAsync(c->d_epack, c->h_epack, sizeof(float) * (size_t)K * epack_stride(c->D),
                                  cudaMemcpyHostToDevice, c->stream));
@@ -259,8 +268,8 @@ static int zero_stats(gmm_ctx* c, int K) {
 // log-likelihood added to stats[K*F].
 static int run_estep(gmm_ctx* c, int K) {
     timer_begin(c, c->t_estep);
-    int rc = use_tensor_estep(c, K) ? tc_launch_estep(c->tc, K, c->d_stats + (size_t)K * c->F, c->stream)
-                                    : launch_estep_simt(c, K);
+    int rc = c->estep_tensor_ready ? tc_launch_estep(c->tc, K, c->d_stats + (size_t)K * c->F, c->stream)
+                                   : launch_estep_simt(c, K);
     timer_end(c, c->t_estep);
     c->memb_valid = (rc == GMM_OK);
     return rc;

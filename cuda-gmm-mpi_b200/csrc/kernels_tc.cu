@@ -17,12 +17,15 @@
 //   warps 4-11  operand builders: centre/scale, form the products, split hi/lo,
 //               write the UMMA operand images (SWIZZLE_NONE core-matrix layout)
 //   warp 1      MMA issuer: 3 x 2 x MT tcgen05.mma (M=128, N=64, K=16) per 32 events
-//   warps 12-15 flush: TMEM accumulators -> FP32 partial sums in an L2-resident
-//               per-CTA scratch every 512 events (the TMEM accumulation truncates:
-//               measured bias -1e-7 per MMA step, see profiles/tc_probe_r1.txt)
+//   warps 12-15 flush: every 128 events the TMEM accumulators are added (FP32, round to
+//               nearest) into register-resident partial sums (setmaxnreg gives this
+//               warpgroup 240 registers) — the TMEM accumulation itself truncates:
+//               measured bias -1e-7 per MMA step (profiles/tc_probe_r1.txt), so the
+//               chains are kept to 24 steps
 // A second tiny kernel reduces the per-CTA partials in double and un-scales.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -52,8 +55,8 @@ using namespace ptx;
 constexpr int kTE = 32;          // events per sub-tile (MMA K extent per operand part)
 constexpr int kNCL = 64;         // clusters per CTA pass (MMA N)
 constexpr int kNST = 3;          // operand stages
-constexpr int kNRAW = 3;         // raw (TMA) stages
-constexpr int kChunkSub = 16;    // sub-tiles between TMEM flushes (512 events)
+constexpr int kNRAW = 4;         // raw (TMA) stages
+constexpr int kChunkSub = 4;     // sub-tiles between TMEM flushes (128 events: 24 MMA steps per accumulator chain)
 constexpr int kMThreads = 512;
 constexpr float kGammaScale = 1024.0f;   // responsibilities are scaled by 2^10 before the FP16 split
 
@@ -72,7 +75,7 @@ template <int D> struct MCfg {
     static constexpr int OFF_RAWX = OFF_G + kNST * G_STAGE;
     static constexpr int OFF_RAWG = OFF_RAWX + kNRAW * RAWX;
     static constexpr int OFF_BAR = OFF_RAWG + kNRAW * RAWG;
-    static constexpr int SMEM_BYTES = OFF_BAR + 256;
+    static constexpr int SMEM_BYTES = OFF_BAR + 512;
     static constexpr int TMEM_COLS = 2 * MT * kNCL;       // two accumulator buffers
 };
 
@@ -142,6 +145,8 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     uint64_t* acc_full = op_empty + kNST;      // [2]
     uint64_t* acc_empty = acc_full + 2;        // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* sh_s = reinterpret_cast<float*>(tmem_slot + 2);     // [D] shift, then [D] inverse scale
+    float* isc_s = sh_s + GMM_MAX_DIMENSIONS;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int e_begin = blockIdx.x * events_per_cta;
@@ -158,13 +163,18 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<512>(tmem_slot);
+    if (threadIdx.x < D) { sh_s[threadIdx.x] = shift_f[threadIdx.x]; isc_s[threadIdx.x] = inv_scale_f[threadIdx.x]; }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 0) {
+    // register re-partition between the warpgroups (64K registers per SM):
+    //   WG0 (TMA / MMA / alloc) 40, WG1-2 (builders) 112, WG3 (flush accumulators) 240
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
             for (int i = 0; i < nsub; i++) {
@@ -176,7 +186,7 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 tma_load_2d(smem + C::OFF_RAWG + st * C::RAWG, &tm_g, e0, k0, &raw_full[st]);
             }
         }
-    } else if (warp == 1) {
+      } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(128, kNCL, /*A MN-major*/ true, /*B MN-major*/ false);
@@ -208,13 +218,12 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 if ((i % kChunkSub) == kChunkSub - 1 || i == nsub - 1) mma_commit(&acc_full[ab]);
             }
         }
-    } else if (warp >= 4 && warp < 12) {
+      }
+    } else if (warp < 12) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
         // ===================== operand builders =====================
         const int part = warp - 4;                 // feature chunks c = part (mod 8)
         const int bt = threadIdx.x - 128;          // 0..255
-        float sh[D], isc[D];
-#pragma unroll
-        for (int d = 0; d < D; d++) { sh[d] = shift_f[d]; isc[d] = inv_scale_f[d]; }
         for (int i = 0; i < nsub; i++) {
             const int rs = i % kNRAW, rph = (i / kNRAW) & 1;
             const int os = i % kNST, oph = (i / kNST) & 1;
@@ -227,10 +236,11 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 #pragma unroll
                 for (int v = 0; v < D / 4; v++) {
                     const float4 t = xr[v];
-                    z[4 * v + 0] = (t.x - sh[4 * v + 0]) * isc[4 * v + 0];
-                    z[4 * v + 1] = (t.y - sh[4 * v + 1]) * isc[4 * v + 1];
-                    z[4 * v + 2] = (t.z - sh[4 * v + 2]) * isc[4 * v + 2];
-                    z[4 * v + 3] = (t.w - sh[4 * v + 3]) * isc[4 * v + 3];
+                    const float4 s4 = reinterpret_cast<const float4*>(sh_s)[v], i4 = reinterpret_cast<const float4*>(isc_s)[v];
+                    z[4 * v + 0] = (t.x - s4.x) * i4.x;
+                    z[4 * v + 1] = (t.y - s4.y) * i4.y;
+                    z[4 * v + 2] = (t.z - s4.z) * i4.z;
+                    z[4 * v + 3] = (t.w - s4.w) * i4.w;
                 }
             }
             uint8_t* phi_hi = smem + C::OFF_PHI + os * C::PHI_STAGE;
@@ -270,41 +280,40 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             __syncwarp();
             if (lane == 0) { mbar_arrive(&op_full[os]); mbar_arrive(&raw_empty[rs]); }
         }
-    } else if (warp >= 12) {
-        // ===================== flush: TMEM -> FP32 partials in the per-CTA scratch =====================
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+        // ===================== flush: TMEM -> register-resident FP32 partial sums =====================
         const int q = warp - 12;                                   // TMEM lane quadrant (= warp % 4)
         const int nchunks = (nsub + kChunkSub - 1) / kChunkSub;
-        float* my = scratch + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * C::MT * 128 + q * 32 + lane) * kNCL;
+        float racc[C::MT * kNCL];
+#pragma unroll
+        for (int j = 0; j < C::MT * kNCL; j++) racc[j] = 0.0f;
         for (int c = 0; c < nchunks; c++) {
             const int ab = c & 1;
             mbar_wait(&acc_full[ab], (c >> 1) & 1);
             tc_fence_after();
 #pragma unroll
             for (int mt = 0; mt < C::MT; mt++) {
-                float4* dst = reinterpret_cast<float4*>(my + (size_t)mt * 128 * kNCL);
 #pragma unroll
                 for (int h = 0; h < kNCL / 32; h++) {
                     uint32_t r[32];
                     tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + ab * (C::MT * kNCL) + mt * kNCL + h * 32, r);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int v = 0; v < 8; v++) {
-                        float4 o = (c == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : dst[h * 8 + v];
-                        o.x += __uint_as_float(r[4 * v + 0]); o.y += __uint_as_float(r[4 * v + 1]);
-                        o.z += __uint_as_float(r[4 * v + 2]); o.w += __uint_as_float(r[4 * v + 3]);
-                        dst[h * 8 + v] = o;
-                    }
+                    for (int j = 0; j < 32; j++) racc[(mt * 2 + h) * 32 + j] += __uint_as_float(r[j]);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[ab]);
         }
-        if (nchunks == 0) {
+        float* my = scratch + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * C::MT * 128 + q * 32 + lane) * kNCL;
 #pragma unroll
-            for (int mt = 0; mt < C::MT; mt++)
-                for (int v = 0; v < kNCL / 4; v++) reinterpret_cast<float4*>(my + (size_t)mt * 128 * kNCL)[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int mt = 0; mt < C::MT; mt++)
+#pragma unroll
+            for (int v = 0; v < kNCL / 4; v++)
+                reinterpret_cast<float4*>(my + (size_t)mt * 128 * kNCL)[v] =
+                    make_float4(racc[mt * kNCL + 4 * v], racc[mt * kNCL + 4 * v + 1], racc[mt * kNCL + 4 * v + 2], racc[mt * kNCL + 4 * v + 3]);
     }
     tc_fence_before();
     __syncthreads();
@@ -331,6 +340,303 @@ __global__ void mstep_tc_finalize_kernel(const float* __restrict__ scratch, int 
     stats[(size_t)k * F + f] += s * fac;
 }
 
+
+// ===========================================================================
+// E-step (estep1 + estep2 of the reference, gaussian_kernel.cu:383-512) on
+// tensor cores.  With Rinv = W^T W (W upper triangular, from the Cholesky
+// factor of Rinv computed on the host) the quadratic form is
+//     q_k(x) = || W_k (x - mu_k) ||^2 = || W'_k z + v_k ||^2 ,   z = (x - shift) * inv_scale,
+// i.e. ONE GEMM  Y[n][(k,d)] = Z~[n][:] . B[(k,d)][:]  with the constant folded in
+// through a ones column, followed by a square-and-sum epilogue, the log-sum-exp
+// over the clusters and the log-likelihood reduction.  Operands are FP16 hi/lo
+// split (z = zh + zl, W' = Wh + Wl); the K dimension concatenates
+//     [ zh | zl | zh | 1 1 0.. ]  x  [ Wh | Wh | Wl | vh vl 0.. ]
+// (the lo*lo product is dropped), FP32 accumulation in TMEM.
+//
+// The whole B operand (all clusters) stays RESIDENT in shared memory: a CTA pair
+// (cta_group::2, M = 256) splits it, each CTA holding half of the N columns of
+// every cluster group, so only event tiles stream (TMA).  Per CTA, 512 threads:
+//   warp 0      TMA producer (raw [128][D] event tile, zero fill beyond n)
+//   warp 1      MMA issuer (leader CTA only): per tile NG groups x KSTEPS tcgen05.mma
+//   warp 2      TMEM allocation
+//   warps 4-7   converters: centre/scale, FP16 hi/lo split, K-major operand image
+//   warps 8-15  epilogue (two warpgroups, even / odd cluster groups): TMEM -> registers,
+//               squares, logits, online max / sum-exp, responsibilities, log-likelihood
+// ===========================================================================
+constexpr int kEThreads = 512;
+
+template <int D> struct ECfg {
+    static_assert(D % 8 == 0, "tensor E-step: D must be a multiple of 8");
+    static constexpr int CP = D / 8;                          // 16-byte K chunks per operand part
+    static constexpr int NCHK = (3 * CP + 1 + 1) / 2 * 2;     // K chunks (even): zh, zl, zh, ones[, pad]
+    static constexpr int KSTEPS = NCHK / 2;
+    static constexpr int G = (D == 24) ? 8 : (D == 16 ? 16 : 32);   // clusters per MMA group
+    static constexpr int N = G * D;                           // MMA N (both CTAs)
+    static constexpr int NH = N / 2;                          // B rows held by each CTA per group
+    static constexpr int GH = G / 2;                          // clusters per CTA per group (B rows only)
+    static constexpr int MAXNG = 64 / G > 0 ? 64 / G : 1;     // up to 64 clusters resident
+    static constexpr int MAXGW = (MAXNG + 1) / 2;             // groups per epilogue warpgroup
+    static constexpr int A_STAGE = NCHK * 128 * 16;
+    static constexpr int B_GROUP = NCHK * NH * 16;            // bytes per group per CTA
+    static constexpr int RAWX = 128 * D * 4;
+    static constexpr int OFF_B = 0;
+    static constexpr int OFF_A = OFF_B + MAXNG * B_GROUP;
+    static constexpr int OFF_RAW = OFF_A + 2 * A_STAGE;
+    static constexpr int OFF_CK = OFF_RAW + 2 * RAWX;         // float[64] constant + ln(pi)
+    static constexpr int OFF_EX = OFF_CK + 256;               // exchange: [2 parity][2 wg][128] x (max, sum)
+    static constexpr int OFF_BAR = OFF_EX + 2 * 2 * 128 * 8;
+    static constexpr int SMEM_BYTES = OFF_BAR + 256;
+    static_assert(N <= 256 && N % 32 == 0, "MMA N");
+    static_assert(2 * N <= 512, "TMEM budget");
+};
+
+template <int D>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kEThreads, 1)
+estep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const uint8_t* __restrict__ b_img, const float* __restrict__ ck,
+                const float* __restrict__ shift_f, const float* __restrict__ inv_scale_f, float* __restrict__ memb,
+                size_t pitch, int n, int K, int NG, double* __restrict__ ll_out) {
+    using C = ECfg<D>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+    uint64_t* raw_full = bars;          // [2]
+    uint64_t* raw_empty = bars + 2;     // [2]
+    uint64_t* a_full = bars + 4;        // [2]  (used in the leader: 8 arrivals = 4 converter warps x 2 CTAs)
+    uint64_t* a_empty = bars + 6;       // [2]  (multicast commit)
+    uint64_t* acc_full = bars + 8;      // [2]  (multicast commit)
+    uint64_t* acc_empty = bars + 10;    // [2]  (used in the leader: 8 arrivals = 4 epilogue warps x 2 CTAs)
+    uint64_t* b_full = bars + 12;       // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    float* ck_s = reinterpret_cast<float*>(smem + C::OFF_CK);
+    float2* ex = reinterpret_cast<float2*>(smem + C::OFF_EX);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int ntiles = (n + 255) / 256;
+    const int my_tiles = pair < ntiles ? (ntiles - pair + npairs - 1) / npairs : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4);
+            mbar_init(&a_full[s], 8); mbar_init(&a_empty[s], 1);
+            mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8);
+        }
+        mbar_init(b_full, 1);
+        fence_mbar_init();
+    }
+    if (threadIdx.x < 64) ck_s[threadIdx.x] = ck[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {                    // resident B: this CTA's half of every cluster group
+        const uint32_t bytes = (uint32_t)NG * C::B_GROUP;
+        mbar_arrive_expect_tx(b_full, bytes);
+        const uint8_t* src = b_img + (size_t)rank * C::MAXNG * C::B_GROUP;
+        for (int g = 0; g < NG; g++) tma_load_1d(smem + C::OFF_B + g * C::B_GROUP, src + (size_t)g * C::B_GROUP, C::B_GROUP, b_full);
+    }
+    if (warp == 2) tmem_alloc_2cta<512>(tmem_slot);
+    mbar_wait(b_full, 0);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            for (int it = 0; it < my_tiles; it++) {
+                const int st = it & 1, ph = (it >> 1) & 1;
+                mbar_wait(&raw_empty[st], ph ^ 1);
+                mbar_arrive_expect_tx(&raw_full[st], C::RAWX);
+                const int e0 = (pair + it * npairs) * 256 + (int)rank * 128;
+                tma_load_2d(smem + C::OFF_RAW + st * C::RAWX, &tm_x, 0, e0, &raw_full[st]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA) =====================
+        if (rank == 0 && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_f16(256, C::N, false, false);
+            uint32_t nuse0 = 0, nuse1 = 0;
+            for (int it = 0; it < my_tiles; it++) {
+                const int as = it & 1, aph = (it >> 1) & 1;
+                mbar_wait_cluster(&a_full[as], aph);
+                tc_fence_after();
+                const uint32_t abase = smem_u32(smem + C::OFF_A + as * C::A_STAGE);
+                for (int g = 0; g < NG; g++) {
+                    const int buf = g & 1;
+                    uint32_t& nuse = buf ? nuse1 : nuse0;
+                    mbar_wait_cluster(&acc_empty[buf], (nuse & 1) ^ 1);
+                    nuse++;
+                    tc_fence_after();
+                    const uint32_t bbase = smem_u32(smem + C::OFF_B + g * C::B_GROUP);
+#pragma unroll
+                    for (int ks = 0; ks < C::KSTEPS; ks++) {
+                        const uint64_t adesc = make_smem_desc(abase + ks * 2 * 2048, /*LBO*/ 2048, /*SBO*/ 128);
+                        const uint64_t bdesc = make_smem_desc(bbase + ks * 2 * (C::NH * 16), /*LBO*/ C::NH * 16, /*SBO*/ 128);
+                        mma_f16_ss_2cta(tmem + buf * C::N, adesc, bdesc, idesc, ks > 0);
+                    }
+                    mma_commit_2cta(&acc_full[buf]);
+                }
+                mma_commit_2cta(&a_empty[as]);
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================== converters =====================
+        const int row = threadIdx.x - 128;
+        float sh[D], isc[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) { sh[d] = shift_f[d]; isc[d] = inv_scale_f[d]; }
+        for (int it = 0; it < my_tiles; it++) {
+            const int st = it & 1, ph = (it >> 1) & 1;
+            mbar_wait(&raw_full[st], ph);
+            mbar_wait(&a_empty[st], ph ^ 1);
+            uint32_t hi[D / 2], lo[D / 2];
+            {
+                const float4* xr = reinterpret_cast<const float4*>(smem + C::OFF_RAW + st * C::RAWX + row * (D * 4));
+#pragma unroll
+                for (int v = 0; v < D / 4; v++) {
+                    const float4 t = xr[v];
+                    const float z0 = (t.x - sh[4 * v + 0]) * isc[4 * v + 0], z1 = (t.y - sh[4 * v + 1]) * isc[4 * v + 1];
+                    const float z2 = (t.z - sh[4 * v + 2]) * isc[4 * v + 2], z3 = (t.w - sh[4 * v + 3]) * isc[4 * v + 3];
+                    const __half2 h01 = __floats2half2_rn(z0, z1), h23 = __floats2half2_rn(z2, z3);
+                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                    hi[2 * v] = *reinterpret_cast<const uint32_t*>(&h01);
+                    hi[2 * v + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                    lo[2 * v] = pack_half2(z0 - f01.x, z1 - f01.y);
+                    lo[2 * v + 1] = pack_half2(z2 - f23.x, z3 - f23.y);
+                }
+            }
+            uint8_t* a = smem + C::OFF_A + st * C::A_STAGE + row * 16;     // K-major: [chunk][row][16 B]
+#pragma unroll
+            for (int c = 0; c < C::CP; c++) {
+                const uint4 h = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                const uint4 l = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                *reinterpret_cast<uint4*>(a + (c) * 2048) = h;
+                *reinterpret_cast<uint4*>(a + (C::CP + c) * 2048) = l;
+                *reinterpret_cast<uint4*>(a + (2 * C::CP + c) * 2048) = h;
+            }
+            *reinterpret_cast<uint4*>(a + (3 * C::CP) * 2048) = make_uint4(0x3C003C00u, 0u, 0u, 0u);      // {1, 1, 0...}
+            if (C::NCHK > 3 * C::CP + 1) *reinterpret_cast<uint4*>(a + (3 * C::CP + 1) * 2048) = make_uint4(0u, 0u, 0u, 0u);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive_cluster(&a_full[st], 0); mbar_arrive(&raw_empty[st]); }
+        }
+    } else if (warp >= 8) {
+        // ===================== epilogue =====================
+        const int wg = (warp - 8) >> 2, q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        double ll_acc = 0.0;
+        uint32_t nfull = 0;
+        for (int it = 0; it < my_tiles; it++) {
+            const int e = (pair + it * npairs) * 256 + (int)rank * 128 + row;
+            float lg[C::MAXGW * C::G];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int gi = 0; gi < C::MAXGW; gi++) {
+                const int g = 2 * gi + wg;
+                if (g < NG) {
+                    mbar_wait_cluster(&acc_full[wg], nfull & 1);
+                    nfull++;
+                    tc_fence_after();
+                    const uint32_t tcol = tmem + lane_base + wg * C::N;
+#pragma unroll
+                    for (int c = 0; c < C::G; c += 2) {
+                        float qv[2];
+                        if constexpr (D == 24) {
+                            uint32_t a0[16], a1[8], b0[16], b1[8];
+                            tmem_ld_32x16(tcol + c * 24, a0); tmem_ld_32x8(tcol + c * 24 + 16, a1);
+                            tmem_ld_32x16(tcol + c * 24 + 24, b0); tmem_ld_32x8(tcol + c * 24 + 40, b1);
+                            tmem_ld_wait();
+                            float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 16; j += 2) {
+                                s0 = fmaf(__uint_as_float(a0[j]), __uint_as_float(a0[j]), s0);
+                                s1 = fmaf(__uint_as_float(a0[j + 1]), __uint_as_float(a0[j + 1]), s1);
+                                t0 = fmaf(__uint_as_float(b0[j]), __uint_as_float(b0[j]), t0);
+                                t1 = fmaf(__uint_as_float(b0[j + 1]), __uint_as_float(b0[j + 1]), t1);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; j += 2) {
+                                s0 = fmaf(__uint_as_float(a1[j]), __uint_as_float(a1[j]), s0);
+                                s1 = fmaf(__uint_as_float(a1[j + 1]), __uint_as_float(a1[j + 1]), s1);
+                                t0 = fmaf(__uint_as_float(b1[j]), __uint_as_float(b1[j]), t0);
+                                t1 = fmaf(__uint_as_float(b1[j + 1]), __uint_as_float(b1[j + 1]), t1);
+                            }
+                            qv[0] = s0 + s1; qv[1] = t0 + t1;
+                        } else {
+                            uint32_t a0[16], b0[16];
+                            static_assert(D == 24 || D == 16 || D == 8, "epilogue load shapes");
+                            if constexpr (D == 16) {
+                                tmem_ld_32x16(tcol + c * 16, a0); tmem_ld_32x16(tcol + c * 16 + 16, b0);
+                            } else {
+                                uint32_t t8a[8], t8b[8];
+                                tmem_ld_32x8(tcol + c * 8, t8a); tmem_ld_32x8(tcol + c * 8 + 8, t8b);
+#pragma unroll
+                                for (int j = 0; j < 8; j++) { a0[j] = t8a[j]; b0[j] = t8b[j]; a0[j + 8] = 0; b0[j + 8] = 0; }
+                            }
+                            tmem_ld_wait();
+                            float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 16; j += 2) {
+                                s0 = fmaf(__uint_as_float(a0[j]), __uint_as_float(a0[j]), s0);
+                                s1 = fmaf(__uint_as_float(a0[j + 1]), __uint_as_float(a0[j + 1]), s1);
+                                t0 = fmaf(__uint_as_float(b0[j]), __uint_as_float(b0[j]), t0);
+                                t1 = fmaf(__uint_as_float(b0[j + 1]), __uint_as_float(b0[j + 1]), t1);
+                            }
+                            qv[0] = s0 + s1; qv[1] = t0 + t1;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 2; u++) {
+                            const float l = fmaf(-0.5f, qv[u], ck_s[g * C::G + c + u]);
+                            lg[gi * C::G + c + u] = l;
+                            mx = fmaxf(mx, l);
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(&acc_empty[wg], 0);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < C::G; c++) lg[gi * C::G + c] = -INFINITY;
+                }
+            }
+            float sm = 0.f;
+            const float mref = (mx == -INFINITY) ? 0.f : mx;         // a warpgroup without any cluster group
+#pragma unroll
+            for (int j = 0; j < C::MAXGW * C::G; j++) sm += expf(lg[j] - mref);
+            float2* exb = ex + (it & 1) * 256;
+            exb[wg * 128 + row] = make_float2(mx, sm);
+            named_bar_sync(1, 256);
+            const float2 o = exb[(wg ^ 1) * 128 + row];
+            const float M = fmaxf(mx, o.x);
+            const float S = sm * expf(mx - M) + o.y * expf(o.x - M);
+            const float denom = M + logf(S);                         // estep2 :490-494
+            if (e < n) {
+                if (wg == 0) ll_acc += (double)denom;
+#pragma unroll
+                for (int gi = 0; gi < C::MAXGW; gi++) {
+                    const int g = 2 * gi + wg;
+#pragma unroll
+                    for (int c = 0; c < C::G; c++) {
+                        const int k = g * C::G + c;
+                        if (g < NG && k < K) memb[(size_t)k * pitch + e] = expf(lg[gi * C::G + c] - denom);   // :498-501
+                    }
+                }
+            }
+        }
+        if (wg == 0) {
+            ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 16);
+            ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 8);
+            ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 4);
+            ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 2);
+            ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 1);
+            if (lane == 0) atomicAdd(ll_out, ll_acc);
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc_2cta<512>(tmem);
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -347,6 +653,16 @@ struct TcState {
     float* d_scratch = nullptr;
     size_t scratch_floats = 0;
     bool have_shift = false;
+    // E-step
+    CUtensorMap tm_x128{};
+    bool emap_ok = false;
+    uint8_t* d_bimg = nullptr;       // [2 ranks][MAXNG * B_GROUP]
+    uint8_t* h_bimg = nullptr;       // pinned
+    size_t bimg_bytes = 0;           // per rank
+    float* d_ck = nullptr;           // [64]
+    float* h_ck = nullptr;           // pinned [64]
+    int e_NG = 0;
+    double h_shift[GMM_MAX_DIMENSIONS] = {0}, h_scale[GMM_MAX_DIMENSIONS] = {0};
 };
 
 static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
@@ -380,7 +696,12 @@ bool tc_mstep_supported(int D, int K) {
     (void)K;
     return D == 4 || D == 8 || D == 12 || D == 16 || D == 20 || D == 24;
 }
-bool tc_estep_supported(int, int) { return false; }
+bool tc_estep_supported(int D, int K) { return (D == 8 || D == 16 || D == 24) && K >= 1 && K <= 64; }
+
+template <int D> static size_t ecfg_bimg_bytes() { return (size_t)ECfg<D>::MAXNG * ECfg<D>::B_GROUP; }
+static size_t bimg_bytes_for(int D) {
+    switch (D) { case 8: return ecfg_bimg_bytes<8>(); case 16: return ecfg_bimg_bytes<16>(); case 24: return ecfg_bimg_bytes<24>(); default: return 0; }
+}
 
 int tc_create(TcState** out, const float* d_x_aos, int n, int D, int Kmax, float* d_memb, size_t memb_pitch, int num_sms,
               cudaStream_t stream) {
@@ -396,6 +717,15 @@ int tc_create(TcState** out, const float* d_x_aos, int n, int D, int Kmax, float
     if (int rc = make_map_2d(&t->tm_x, d_x_aos, (uint64_t)D, (uint64_t)n, (uint64_t)D * 4, (uint32_t)D, kTE)) return rc;
     if (int rc = make_map_2d(&t->tm_g, d_memb, (uint64_t)n, (uint64_t)Kmax, (uint64_t)memb_pitch * 4, kTE, kNCL)) return rc;
     t->maps_ok = true;
+    if (D == 8 || D == 16 || D == 24) {
+        if (int rc = make_map_2d(&t->tm_x128, d_x_aos, (uint64_t)D, (uint64_t)n, (uint64_t)D * 4, (uint32_t)D, 128)) return rc;
+        t->bimg_bytes = bimg_bytes_for(D);
+        TC_CUDA_TRY(cudaMalloc(&t->d_bimg, 2 * t->bimg_bytes));
+        TC_CUDA_TRY(cudaMallocHost(&t->h_bimg, 2 * t->bimg_bytes));
+        TC_CUDA_TRY(cudaMalloc(&t->d_ck, sizeof(float) * 64));
+        TC_CUDA_TRY(cudaMallocHost(&t->h_ck, sizeof(float) * 64));
+        t->emap_ok = true;
+    }
     const int mt = (num_features(D) + 127) / 128;
     const int ytiles = (Kmax + kNCL - 1) / kNCL;
     t->scratch_floats = (size_t)num_sms * ytiles * mt * 128 * kNCL;
@@ -406,6 +736,9 @@ int tc_create(TcState** out, const float* d_x_aos, int n, int D, int Kmax, float
 void tc_destroy(TcState* t) {
     if (!t) return;
     cudaFree(t->d_shift_f); cudaFree(t->d_inv_scale_f); cudaFree(t->d_scale); cudaFree(t->d_scratch);
+    cudaFree(t->d_bimg); cudaFree(t->d_ck);
+    if (t->h_bimg) cudaFreeHost(t->h_bimg);
+    if (t->h_ck) cudaFreeHost(t->h_ck);
     delete t;
 }
 
@@ -419,6 +752,8 @@ int tc_set_shift_scale(TcState* t, double* shift, const double* scale, cudaStrea
         const double s = (scale && scale[d] > 0) ? scale[d] : 1.0;
         isf[d] = (float)(1.0 / s);
         sc[d] = 1.0 / (double)isf[d];
+        t->h_shift[d] = shift[d];
+        t->h_scale[d] = sc[d];
     }
     TC_CUDA_TRY(cudaMemcpyAsync(t->d_shift_f, sf, sizeof(sf), cudaMemcpyHostToDevice, stream));
     TC_CUDA_TRY(cudaMemcpyAsync(t->d_inv_scale_f, isf, sizeof(isf), cudaMemcpyHostToDevice, stream));
@@ -428,8 +763,114 @@ int tc_set_shift_scale(TcState* t, double* shift, const double* scale, cudaStrea
     return GMM_OK;
 }
 
-int tc_upload_params(TcState*, const clusters_t*, int, cudaStream_t) { return GMM_OK; }
-int tc_launch_estep(TcState*, int, double*, cudaStream_t) { return fail(GMM_ERR_STATE, "tensor-core E-step not available"); }
+// Host side of the tensor E-step operand: per cluster the upper-triangular factor W of
+// Rinv = W^T W (Cholesky of the symmetrised inverse covariance, double), expressed in the
+// centred/scaled coordinates of the kernel, FP16 hi/lo split, laid out as the resident
+// K-major B image of each CTA of the pair.  Fails (GMM_ERR_STATE) when Rinv is not positive
+// definite or the factor overflows FP16; the caller then uses the SIMT kernel for this state.
+template <int D>
+static int build_bimg(TcState* t, const clusters_t* host, int K) {
+    using C = ECfg<D>;
+    const int NG = (K + C::G - 1) / C::G;
+    std::memset(t->h_bimg, 0, 2 * t->bimg_bytes);
+    for (int k = 0; k < 64; k++) t->h_ck[k] = -1e30f;
+    auto put = [&](int rank, int g, int chunk, int rowh, int elem, float v) {
+        __half h = __float2half_rn(v);
+        uint8_t* p = t->h_bimg + (size_t)rank * t->bimg_bytes + (size_t)g * C::B_GROUP + (size_t)chunk * C::NH * 16 + (size_t)rowh * 16 + elem * 2;
+        std::memcpy(p, &h, 2);
+    };
+    for (int k = 0; k < K; k++) {
+        double A[D][D], Gc[D][D];
+        const float* Ri = host->Rinv + (size_t)k * D * D;
+        for (int i = 0; i < D; i++)
+            for (int j = 0; j < D; j++) { A[i][j] = 0.5 * ((double)Ri[i * D + j] + (double)Ri[j * D + i]); Gc[i][j] = 0.0; }
+        for (int j = 0; j < D; j++) {                       // Cholesky A = Gc Gc^T
+            double d = A[j][j];
+            for (int p = 0; p < j; p++) d -= Gc[j][p] * Gc[j][p];
+            if (!(d > 0.0) || !std::isfinite(d)) return fail(GMM_ERR_STATE, "tensor E-step: inverse covariance of a cluster is not positive definite");
+            Gc[j][j] = std::sqrt(d);
+            for (int i = j + 1; i < D; i++) {
+                double v = A[i][j];
+                for (int p = 0; p < j; p++) v -= Gc[i][p] * Gc[j][p];
+                Gc[i][j] = v / Gc[j][j];
+            }
+        }
+        const int g = k / C::G, cg = k % C::G;
+        for (int d = 0; d < D; d++) {
+            // row d of W = Gc^T:  W[d][j] = Gc[j][d] (j >= d);  y_d = sum_j W'[d][j] z_j + v_d
+            double vd = 0.0;
+            const int ncol = cg * D + d;                     // MMA column inside the group
+            const int rank = ncol / C::NH, rowh = ncol % C::NH;
+            for (int j = 0; j < D; j++) {
+                const double w = (j >= d) ? Gc[j][d] : 0.0;
+                const double wp = w * t->h_scale[j];
+                vd -= w * ((double)host->means[(size_t)k * D + j] - t->h_shift[j]);
+                const float wf = (float)wp;
+                if (!(std::fabs(wf) < 6.0e4f)) return fail(GMM_ERR_STATE, "tensor E-step: whitening factor exceeds the FP16 range");
+                const float wh = __half2float(__float2half_rn(wf));
+                const float wl = (float)(wp - (double)wh);
+                const int c = j / 8, e = j % 8;
+                put(rank, g, c, rowh, e, wh);                 // x zh
+                put(rank, g, C::CP + c, rowh, e, wh);         // x zl
+                put(rank, g, 2 * C::CP + c, rowh, e, wl);     // x zh (low part of W')
+            }
+            const float vf = (float)vd;
+            if (!(std::fabs(vf) < 6.0e4f)) return fail(GMM_ERR_STATE, "tensor E-step: offset exceeds the FP16 range");
+            const float vh = __half2float(__float2half_rn(vf));
+            put(rank, g, 3 * C::CP, rowh, 0, vh);
+            put(rank, g, 3 * C::CP, rowh, 1, (float)(vd - (double)vh));
+        }
+        t->h_ck[k] = host->constant[k] + logf(host->pi[k]);  // additive term of estep1 (gaussian_kernel.cu:442)
+    }
+    t->e_NG = NG;
+    return GMM_OK;
+}
+
+int tc_upload_params(TcState* t, const clusters_t* host, int K, cudaStream_t stream) {
+    if (!t || !t->emap_ok) return fail(GMM_ERR_STATE, "tensor E-step not initialised for this shape");
+    if (!t->have_shift) return fail(GMM_ERR_STATE, "tensor E-step needs the global moments (shift/scale) first");
+    TC_CUDA_TRY(cudaStreamSynchronize(stream));          // the pinned staging buffers may still be in flight
+    int rc;
+    switch (t->D) {
+        case 8: rc = build_bimg<8>(t, host, K); break;
+        case 16: rc = build_bimg<16>(t, host, K); break;
+        case 24: rc = build_bimg<24>(t, host, K); break;
+        default: return fail(GMM_ERR_ARG, "tensor E-step: unsupported D");
+    }
+    if (rc) return rc;
+    TC_CUDA_TRY(cudaMemcpyAsync(t->d_bimg, t->h_bimg, 2 * t->bimg_bytes, cudaMemcpyHostToDevice, stream));
+    TC_CUDA_TRY(cudaMemcpyAsync(t->d_ck, t->h_ck, sizeof(float) * 64, cudaMemcpyHostToDevice, stream));
+    return GMM_OK;
+}
+
+template <int D>
+static int launch_estep_d(TcState* t, int K, double* d_ll, cudaStream_t stream) {
+    using C = ECfg<D>;
+    static_assert(C::SMEM_BYTES <= 232448, "shared memory budget");
+    static bool attr = false;
+    if (!attr) {
+        TC_CUDA_TRY(cudaFuncSetAttribute(estep_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr = true;
+    }
+    const int ntiles = (t->n + 255) / 256;
+    int pairs = t->num_sms / 2;
+    if (pairs > ntiles) pairs = ntiles;
+    if (pairs < 1) pairs = 1;
+    estep_tc_kernel<D><<<2 * pairs, kEThreads, C::SMEM_BYTES, stream>>>(t->tm_x128, t->d_bimg, t->d_ck, t->d_shift_f, t->d_inv_scale_f,
+                                                                        t->d_memb, t->memb_pitch, t->n, K, t->e_NG, d_ll);
+    TC_CUDA_TRY(cudaGetLastError());
+    return GMM_OK;
+}
+
+int tc_launch_estep(TcState* t, int K, double* d_ll, cudaStream_t stream) {
+    if (!t || !t->emap_ok) return fail(GMM_ERR_STATE, "tensor E-step not initialised for this shape");
+    switch (t->D) {
+        case 8: return launch_estep_d<8>(t, K, d_ll, stream);
+        case 16: return launch_estep_d<16>(t, K, d_ll, stream);
+        case 24: return launch_estep_d<24>(t, K, d_ll, stream);
+        default: return fail(GMM_ERR_ARG, "tensor E-step: unsupported D");
+    }
+}
 
 template <int D>
 static int launch_mstep_d(TcState* t, int K, double* d_stats, cudaStream_t stream) {

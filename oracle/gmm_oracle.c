@@ -90,7 +90,7 @@ void oracle_transpose(const float* aos, int N, int D, float* soa) {
  * In-place Crout LU without pivoting; expressions kept literally (including
  * the double-typed 1.0 literals).
  * ------------------------------------------------------------------------- */
-void oracle_invert(float* data, int actualsize, float* log_determinant, int use_log10) {
+static void invert_literal(float* data, int actualsize, float* log_determinant, int use_log10) {
     int maxsize = actualsize;
     int n = actualsize;
     *log_determinant = 0.0;
@@ -141,6 +141,72 @@ void oracle_invert(float* data, int actualsize, float* log_determinant, int use_
                 data[j * maxsize + i] = sum;
             }
     }
+}
+
+static void invert_exact(double* data, int actualsize, double* log_determinant, int use_log10) {
+    int maxsize = actualsize;
+    int n = actualsize;
+    *log_determinant = 0.0;
+    if (actualsize == 1) {
+        *log_determinant = log(data[0]);
+        data[0] = 1.0 / data[0];
+    } else if (actualsize >= 2) {
+        for (int i = 1; i < actualsize; i++) data[i] /= data[0];
+        for (int i = 1; i < actualsize; i++) {
+            for (int j = i; j < actualsize; j++) {
+                double sum = 0.0;
+                for (int k = 0; k < i; k++) sum += data[j * maxsize + k] * data[k * maxsize + i];
+                data[j * maxsize + i] -= sum;
+            }
+            if (i == actualsize - 1) continue;
+            for (int j = i + 1; j < actualsize; j++) {
+                double sum = 0.0;
+                for (int k = 0; k < i; k++) sum += data[i * maxsize + k] * data[k * maxsize + j];
+                data[i * maxsize + j] = (data[i * maxsize + j] - sum) / data[i * maxsize + i];
+            }
+        }
+        for (int i = 0; i < actualsize; i++) {
+            if (use_log10) *log_determinant += log10(fabs(data[i * n + i]));   /* invert_matrix.cpp:61 */
+            else           *log_determinant += log(fabs(data[i * n + i]));    /* gaussian_kernel.cu:139 */
+        }
+        for (int i = 0; i < actualsize; i++)
+            for (int j = i; j < actualsize; j++) {
+                double x = 1.0;
+                if (i != j) {
+                    x = 0.0;
+                    for (int k = i; k < j; k++) x -= data[j * maxsize + k] * data[k * maxsize + i];
+                }
+                data[j * maxsize + i] = x / data[j * maxsize + j];
+            }
+        for (int i = 0; i < actualsize; i++)
+            for (int j = i; j < actualsize; j++) {
+                if (i == j) continue;
+                double sum = 0.0;
+                for (int k = i; k < j; k++)
+                    sum += data[k * maxsize + j] * ((i == k) ? 1.0 : data[i * maxsize + k]);
+                data[i * maxsize + j] = -sum;
+            }
+        for (int i = 0; i < actualsize; i++)
+            for (int j = 0; j < actualsize; j++) {
+                double sum = 0.0;
+                for (int k = ((i > j) ? i : j); k < actualsize; k++)
+                    sum += ((j == k) ? 1.0 : data[j * maxsize + k]) * data[k * maxsize + i];
+                data[j * maxsize + i] = sum;
+            }
+    }
+}
+
+/* ORACLE_REAL=float : the reference's FP32 routine, literally.
+ * ORACLE_REAL=double: the same elimination (no pivoting) carried out in double on the float
+ * input and rounded back to float — the ground-truth build removes the reference's FP32
+ * round-off from the inverse (the float LU alone perturbs Rinv by ~cond*2^-24*D). */
+void oracle_invert(float* data, int actualsize, float* log_determinant, int use_log10) {
+    if (sizeof(real) == 4) { invert_literal(data, actualsize, log_determinant, use_log10); return; }
+    double m[32 * 32], ld;
+    for (int i = 0; i < actualsize * actualsize; i++) m[i] = data[i];
+    invert_exact(m, actualsize, &ld, use_log10);
+    for (int i = 0; i < actualsize * actualsize; i++) data[i] = (float)m[i];
+    *log_determinant = (float)ld;
 }
 
 /* ---------------------------------------------------------------------------
