@@ -412,6 +412,7 @@ int gmm_create(gmm_ctx** out, int device, int n_local, int D, int Kmax, const fl
     {
         int rc = tc_create(&c->tc, c->d_x_aos, n_local, D, Kmax, c->d_memb, c->memb_pitch, c->num_sms, c->stream);
         if (rc) { gmm_destroy(c); return rc; }
+        tc_set_host_threads(c->tc, c->host_threads);
     }
     CREATE_TRY(cudaStreamSynchronize(c->stream));
 #undef CREATE_TRY
@@ -472,7 +473,7 @@ int gmm_set_option(gmm_ctx* c, const char* key, double value) {
         if (p < GMM_PATH_AUTO || p > GMM_PATH_TENSOR) return fail(GMM_ERR_ARG, "gmm_set_option: bad path");
         c->path = p;
     } else if (k == "verbose") c->verbose = (int)value;
-    else if (k == "host_threads") c->host_threads = value < 1 ? 1 : (int)value;
+    else if (k == "host_threads") { c->host_threads = value < 1 ? 1 : (int)value; tc_set_host_threads(c->tc, c->host_threads); }
     else if (k == "write_memberships") { /* accepted; every E-step materialises memberships in this build */ }
     else return fail(GMM_ERR_ARG, "gmm_set_option: unknown key '" + k + "'");
     return GMM_OK;

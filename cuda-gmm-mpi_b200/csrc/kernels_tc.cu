@@ -133,7 +133,7 @@ __device__ __forceinline__ void build_phi_chunks(const float (&z)[D], uint8_t* h
 template <int D>
 __global__ void __launch_bounds__(kMThreads, 1)
 mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g, int n,
-                const float* __restrict__ shift_f, const float* __restrict__ inv_scale_f, float* __restrict__ scratch,
+                const float* __restrict__ shift_f, const float* __restrict__ inv_scale_f, double* __restrict__ scratch,
                 int events_per_cta) {
     using C = MCfg<D>;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -145,7 +145,7 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     uint64_t* acc_full = op_empty + kNST;      // [2]
     uint64_t* acc_empty = acc_full + 2;        // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    float* sh_s = reinterpret_cast<float*>(tmem_slot + 2);     // [D] shift, then [D] inverse scale
+    float* sh_s = reinterpret_cast<float*>(smem + C::OFF_BAR + 192);   // [32] shift, then [32] inverse scale (16-byte aligned)
     float* isc_s = sh_s + GMM_MAX_DIMENSIONS;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -288,32 +288,48 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         float racc[C::MT * kNCL];
 #pragma unroll
         for (int j = 0; j < C::MT * kNCL; j++) racc[j] = 0.0f;
-        for (int c = 0; c < nchunks; c++) {
-            const int ab = c & 1;
-            mbar_wait(&acc_full[ab], (c >> 1) & 1);
-            tc_fence_after();
+        // second level: every kSpill chunks the FP32 partial sums move into this thread's double
+        // partials in the (L2-resident) per-CTA scratch, bounding the FP32 random walk to kSpill adds
+        constexpr int kSpill = 16;
+        double* my = scratch + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * C::MT * 128 + q * 32 + lane) * kNCL;
+        bool spilled = false;
+        for (int c = 0; c < nchunks || !spilled; c++) {
+            if (c < nchunks) {
+                const int ab = c & 1;
+                mbar_wait(&acc_full[ab], (c >> 1) & 1);
+                tc_fence_after();
 #pragma unroll
-            for (int mt = 0; mt < C::MT; mt++) {
+                for (int mt = 0; mt < C::MT; mt++) {
 #pragma unroll
-                for (int h = 0; h < kNCL / 32; h++) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + ab * (C::MT * kNCL) + mt * kNCL + h * 32, r);
-                    tmem_ld_wait();
+                    for (int h = 0; h < kNCL / 32; h++) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + ab * (C::MT * kNCL) + mt * kNCL + h * 32, r);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; j++) racc[(mt * 2 + h) * 32 + j] += __uint_as_float(r[j]);
+                        for (int j = 0; j < 32; j++) racc[(mt * 2 + h) * 32 + j] += __uint_as_float(r[j]);
+                    }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[ab]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[ab]);
+            if ((c % kSpill) == kSpill - 1 || c >= nchunks - 1) {
+#pragma unroll
+                for (int mt = 0; mt < C::MT; mt++) {
+                    double2* dst = reinterpret_cast<double2*>(my + (size_t)mt * 128 * kNCL);
+#pragma unroll
+                    for (int v = 0; v < kNCL / 2; v++) {
+                        double2 o = spilled ? dst[v] : make_double2(0.0, 0.0);
+                        o.x += (double)racc[mt * kNCL + 2 * v];
+                        o.y += (double)racc[mt * kNCL + 2 * v + 1];
+                        dst[v] = o;
+                        racc[mt * kNCL + 2 * v] = 0.0f;
+                        racc[mt * kNCL + 2 * v + 1] = 0.0f;
+                    }
+                }
+                spilled = true;
+            }
         }
-        float* my = scratch + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * C::MT * 128 + q * 32 + lane) * kNCL;
-#pragma unroll
-        for (int mt = 0; mt < C::MT; mt++)
-#pragma unroll
-            for (int v = 0; v < kNCL / 4; v++)
-                reinterpret_cast<float4*>(my + (size_t)mt * 128 * kNCL)[v] =
-                    make_float4(racc[mt * kNCL + 4 * v], racc[mt * kNCL + 4 * v + 1], racc[mt * kNCL + 4 * v + 2], racc[mt * kNCL + 4 * v + 3]);
     }
     tc_fence_before();
     __syncthreads();
@@ -321,7 +337,7 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 }
 
 // Reduce the per-CTA FP32 partials in double, undo the operand scaling and write the packed statistics.
-__global__ void mstep_tc_finalize_kernel(const float* __restrict__ scratch, int ncta_x, int MT, int K, int D, int F,
+__global__ void mstep_tc_finalize_kernel(const double* __restrict__ scratch, int ncta_x, int MT, int K, int D, int F,
                                          const double* __restrict__ scale, double* __restrict__ stats) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= K * F) return;
@@ -329,7 +345,7 @@ __global__ void mstep_tc_finalize_kernel(const float* __restrict__ scratch, int 
     const int ty = k / kNCL, col = k % kNCL, mt = f / 128, row = f % 128;
     double s = 0;
     for (int cx = 0; cx < ncta_x; cx++)
-        s += (double)scratch[(((size_t)(ty * ncta_x + cx) * MT + mt) * 128 + row) * kNCL + col];
+        s += scratch[(((size_t)(ty * ncta_x + cx) * MT + mt) * 128 + row) * kNCL + col];
     double fac = 1.0 / (double)kGammaScale;
     if (f >= 1 && f <= D) fac *= scale[f - 1];
     else if (f > D) {
@@ -385,7 +401,7 @@ template <int D> struct ECfg {
     static constexpr int OFF_CK = OFF_RAW + 2 * RAWX;         // float[64] constant + ln(pi)
     static constexpr int OFF_EX = OFF_CK + 256;               // exchange: [2 parity][2 wg][128] x (max, sum)
     static constexpr int OFF_BAR = OFF_EX + 2 * 2 * 128 * 8;
-    static constexpr int SMEM_BYTES = OFF_BAR + 256;
+    static constexpr int SMEM_BYTES = OFF_BAR + 512;
     static_assert(N <= 256 && N % 32 == 0, "MMA N");
     static_assert(2 * N <= 512, "TMEM budget");
 };
@@ -408,6 +424,8 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const uint8_t* __restr
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
     float* ck_s = reinterpret_cast<float*>(smem + C::OFF_CK);
     float2* ex = reinterpret_cast<float2*>(smem + C::OFF_EX);
+    float* sh_s = reinterpret_cast<float*>(smem + C::OFF_BAR + 128);   // [32] shift, [32] inverse scale
+    float* isc_s = sh_s + 32;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -425,6 +443,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const uint8_t* __restr
         fence_mbar_init();
     }
     if (threadIdx.x < 64) ck_s[threadIdx.x] = ck[threadIdx.x];
+    if (threadIdx.x < D) { sh_s[threadIdx.x] = shift_f[threadIdx.x]; isc_s[threadIdx.x] = inv_scale_f[threadIdx.x]; }
     __syncthreads();
     if (threadIdx.x == 0) {                    // resident B: this CTA's half of every cluster group
         const uint32_t bytes = (uint32_t)NG * C::B_GROUP;
@@ -439,7 +458,10 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const uint8_t* __restr
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 0) {
+    // register re-partition (64K per SM): WG0 (TMA / MMA / alloc) 40, WG1 (converters) 72, WG2-3 (epilogue) 200
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
             for (int it = 0; it < my_tiles; it++) {
@@ -450,7 +472,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const uint8_t* __restr
                 tma_load_2d(smem + C::OFF_RAW + st * C::RAWX, &tm_x, 0, e0, &raw_full[st]);
             }
         }
-    } else if (warp == 1) {
+      } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA) =====================
         if (rank == 0 && elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(256, C::N, false, false);
@@ -478,12 +500,11 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const uint8_t* __restr
                 mma_commit_2cta(&a_empty[as]);
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+      }
+    } else if (warp < 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
         // ===================== converters =====================
         const int row = threadIdx.x - 128;
-        float sh[D], isc[D];
-#pragma unroll
-        for (int d = 0; d < D; d++) { sh[d] = shift_f[d]; isc[d] = inv_scale_f[d]; }
         for (int it = 0; it < my_tiles; it++) {
             const int st = it & 1, ph = (it >> 1) & 1;
             mbar_wait(&raw_full[st], ph);
@@ -494,8 +515,9 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const uint8_t* __restr
 #pragma unroll
                 for (int v = 0; v < D / 4; v++) {
                     const float4 t = xr[v];
-                    const float z0 = (t.x - sh[4 * v + 0]) * isc[4 * v + 0], z1 = (t.y - sh[4 * v + 1]) * isc[4 * v + 1];
-                    const float z2 = (t.z - sh[4 * v + 2]) * isc[4 * v + 2], z3 = (t.w - sh[4 * v + 3]) * isc[4 * v + 3];
+                    const float4 s4 = reinterpret_cast<const float4*>(sh_s)[v], i4 = reinterpret_cast<const float4*>(isc_s)[v];
+                    const float z0 = (t.x - s4.x) * i4.x, z1 = (t.y - s4.y) * i4.y;
+                    const float z2 = (t.z - s4.z) * i4.z, z3 = (t.w - s4.w) * i4.w;
                     const __half2 h01 = __floats2half2_rn(z0, z1), h23 = __floats2half2_rn(z2, z3);
                     const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
                     hi[2 * v] = *reinterpret_cast<const uint32_t*>(&h01);
@@ -519,11 +541,14 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const uint8_t* __restr
             __syncwarp();
             if (lane == 0) { mbar_arrive_cluster(&a_full[st], 0); mbar_arrive(&raw_empty[st]); }
         }
-    } else if (warp >= 8) {
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
         // ===================== epilogue =====================
         const int wg = (warp - 8) >> 2, q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        constexpr int PC = 2 * D;                               // TMEM columns of one cluster pair
+        constexpr int NPAIR = C::G / 2;
         double ll_acc = 0.0;
         uint32_t nfull = 0;
         for (int it = 0; it < my_tiles; it++) {
@@ -538,78 +563,60 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const uint8_t* __restr
                     nfull++;
                     tc_fence_after();
                     const uint32_t tcol = tmem + lane_base + wg * C::N;
-#pragma unroll
-                    for (int c = 0; c < C::G; c += 2) {
-                        float qv[2];
+                    uint32_t v[2][PC];                           // ping-pong register sets, one cluster pair each
+                    auto load_pair = [&](int p, uint32_t (&dst)[PC]) {
                         if constexpr (D == 24) {
-                            uint32_t a0[16], a1[8], b0[16], b1[8];
-                            tmem_ld_32x16(tcol + c * 24, a0); tmem_ld_32x8(tcol + c * 24 + 16, a1);
-                            tmem_ld_32x16(tcol + c * 24 + 24, b0); tmem_ld_32x8(tcol + c * 24 + 40, b1);
-                            tmem_ld_wait();
-                            float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
-#pragma unroll
-                            for (int j = 0; j < 16; j += 2) {
-                                s0 = fmaf(__uint_as_float(a0[j]), __uint_as_float(a0[j]), s0);
-                                s1 = fmaf(__uint_as_float(a0[j + 1]), __uint_as_float(a0[j + 1]), s1);
-                                t0 = fmaf(__uint_as_float(b0[j]), __uint_as_float(b0[j]), t0);
-                                t1 = fmaf(__uint_as_float(b0[j + 1]), __uint_as_float(b0[j + 1]), t1);
-                            }
-#pragma unroll
-                            for (int j = 0; j < 8; j += 2) {
-                                s0 = fmaf(__uint_as_float(a1[j]), __uint_as_float(a1[j]), s0);
-                                s1 = fmaf(__uint_as_float(a1[j + 1]), __uint_as_float(a1[j + 1]), s1);
-                                t0 = fmaf(__uint_as_float(b1[j]), __uint_as_float(b1[j]), t0);
-                                t1 = fmaf(__uint_as_float(b1[j + 1]), __uint_as_float(b1[j + 1]), t1);
-                            }
-                            qv[0] = s0 + s1; qv[1] = t0 + t1;
+                            tmem_ld_32x32(tcol + p * PC, *reinterpret_cast<uint32_t(*)[32]>(&dst[0]));
+                            tmem_ld_32x16(tcol + p * PC + 32, *reinterpret_cast<uint32_t(*)[16]>(&dst[32]));
+                        } else if constexpr (D == 16) {
+                            tmem_ld_32x32(tcol + p * PC, *reinterpret_cast<uint32_t(*)[32]>(&dst[0]));
                         } else {
-                            uint32_t a0[16], b0[16];
-                            static_assert(D == 24 || D == 16 || D == 8, "epilogue load shapes");
-                            if constexpr (D == 16) {
-                                tmem_ld_32x16(tcol + c * 16, a0); tmem_ld_32x16(tcol + c * 16 + 16, b0);
-                            } else {
-                                uint32_t t8a[8], t8b[8];
-                                tmem_ld_32x8(tcol + c * 8, t8a); tmem_ld_32x8(tcol + c * 8 + 8, t8b);
+                            tmem_ld_32x16(tcol + p * PC, *reinterpret_cast<uint32_t(*)[16]>(&dst[0]));
+                        }
+                    };
+                    load_pair(0, v[0]);
+                    tmem_ld_wait();
 #pragma unroll
-                                for (int j = 0; j < 8; j++) { a0[j] = t8a[j]; b0[j] = t8b[j]; a0[j + 8] = 0; b0[j + 8] = 0; }
-                            }
-                            tmem_ld_wait();
-                            float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
-#pragma unroll
-                            for (int j = 0; j < 16; j += 2) {
-                                s0 = fmaf(__uint_as_float(a0[j]), __uint_as_float(a0[j]), s0);
-                                s1 = fmaf(__uint_as_float(a0[j + 1]), __uint_as_float(a0[j + 1]), s1);
-                                t0 = fmaf(__uint_as_float(b0[j]), __uint_as_float(b0[j]), t0);
-                                t1 = fmaf(__uint_as_float(b0[j + 1]), __uint_as_float(b0[j + 1]), t1);
-                            }
-                            qv[0] = s0 + s1; qv[1] = t0 + t1;
+                    for (int p = 0; p < NPAIR; p++) {
+                        if (p + 1 < NPAIR) load_pair(p + 1, v[(p + 1) & 1]);
+                        else {                                   // every column of this buffer has been read
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster(&acc_empty[wg], 0);
                         }
 #pragma unroll
                         for (int u = 0; u < 2; u++) {
-                            const float l = fmaf(-0.5f, qv[u], ck_s[g * C::G + c + u]);
-                            lg[gi * C::G + c + u] = l;
+                            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                            for (int j = 0; j < D; j += 4) {
+                                const float y0 = __uint_as_float(v[p & 1][u * D + j]), y1 = __uint_as_float(v[p & 1][u * D + j + 1]);
+                                const float y2 = __uint_as_float(v[p & 1][u * D + j + 2]), y3 = __uint_as_float(v[p & 1][u * D + j + 3]);
+                                s0 = fmaf(y0, y0, s0); s1 = fmaf(y1, y1, s1); s2 = fmaf(y2, y2, s2); s3 = fmaf(y3, y3, s3);
+                            }
+                            const float l = fmaf(-0.5f, (s0 + s1) + (s2 + s3), ck_s[g * C::G + 2 * p + u]);
+                            lg[gi * C::G + 2 * p + u] = l;
                             mx = fmaxf(mx, l);
                         }
+                        if (p + 1 < NPAIR) tmem_ld_wait();
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(&acc_empty[wg], 0);
                 } else {
 #pragma unroll
                     for (int c = 0; c < C::G; c++) lg[gi * C::G + c] = -INFINITY;
                 }
             }
+            // log-sum-exp over the clusters (estep2, gaussian_kernel.cu:481-503): local part, then the two warpgroups combine
             float sm = 0.f;
             const float mref = (mx == -INFINITY) ? 0.f : mx;         // a warpgroup without any cluster group
 #pragma unroll
-            for (int j = 0; j < C::MAXGW * C::G; j++) sm += expf(lg[j] - mref);
+            for (int j = 0; j < C::MAXGW * C::G; j++) { lg[j] = __expf(lg[j] - mref); sm += lg[j]; }
             float2* exb = ex + (it & 1) * 256;
             exb[wg * 128 + row] = make_float2(mx, sm);
             named_bar_sync(1, 256);
             const float2 o = exb[(wg ^ 1) * 128 + row];
             const float M = fmaxf(mx, o.x);
-            const float S = sm * expf(mx - M) + o.y * expf(o.x - M);
-            const float denom = M + logf(S);                         // estep2 :490-494
+            const float S = sm * __expf(mx - M) + o.y * __expf(o.x - M);
+            const float denom = M + logf(S);                         // :490-494
+            const float scale = __expf(mref - M) / S;                // exp(l - denom) = exp(l - mref) * exp(mref - M) / S
             if (e < n) {
                 if (wg == 0) ll_acc += (double)denom;
 #pragma unroll
@@ -618,7 +625,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const uint8_t* __restr
 #pragma unroll
                     for (int c = 0; c < C::G; c++) {
                         const int k = g * C::G + c;
-                        if (g < NG && k < K) memb[(size_t)k * pitch + e] = expf(lg[gi * C::G + c] - denom);   // :498-501
+                        if (g < NG && k < K) memb[(size_t)k * pitch + e] = lg[gi * C::G + c] * scale;   // :498-501
                     }
                 }
             }
@@ -650,7 +657,7 @@ struct TcState {
     float* d_shift_f = nullptr;      // [32]
     float* d_inv_scale_f = nullptr;  // [32]
     double* d_scale = nullptr;       // [32] = 1 / inv_scale_f (double)
-    float* d_scratch = nullptr;
+    double* d_scratch = nullptr;
     size_t scratch_floats = 0;
     bool have_shift = false;
     // E-step
@@ -662,6 +669,7 @@ struct TcState {
     float* d_ck = nullptr;           // [64]
     float* h_ck = nullptr;           // pinned [64]
     int e_NG = 0;
+    int host_threads = 8;
     double h_shift[GMM_MAX_DIMENSIONS] = {0}, h_scale[GMM_MAX_DIMENSIONS] = {0};
 };
 
@@ -729,9 +737,11 @@ int tc_create(TcState** out, const float* d_x_aos, int n, int D, int Kmax, float
     const int mt = (num_features(D) + 127) / 128;
     const int ytiles = (Kmax + kNCL - 1) / kNCL;
     t->scratch_floats = (size_t)num_sms * ytiles * mt * 128 * kNCL;
-    TC_CUDA_TRY(cudaMalloc(&t->d_scratch, sizeof(float) * t->scratch_floats));
+    TC_CUDA_TRY(cudaMalloc(&t->d_scratch, sizeof(double) * t->scratch_floats));
     return GMM_OK;
 }
+
+void tc_set_host_threads(TcState* t, int n) { if (t) t->host_threads = n < 1 ? 1 : n; }
 
 void tc_destroy(TcState* t) {
     if (!t) return;
@@ -768,26 +778,65 @@ int tc_set_shift_scale(TcState* t, double* shift, const double* scale, cudaStrea
 // centred/scaled coordinates of the kernel, FP16 hi/lo split, laid out as the resident
 // K-major B image of each CTA of the pair.  Fails (GMM_ERR_STATE) when Rinv is not positive
 // definite or the factor overflows FP16; the caller then uses the SIMT kernel for this state.
+// float -> IEEE half bits, round to nearest even (normal, subnormal and zero; callers check the range)
+static inline uint16_t f2h_bits(float f) {
+    uint32_t x;
+    std::memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    x &= 0x7fffffffu;
+    if (x >= 0x47800000u) return (uint16_t)(sign | 0x7c00u);
+    if (x < 0x38800000u) {                      // below the smallest normal half: value * 2^24, rounded
+        float a;
+        std::memcpy(&a, &x, 4);
+        return (uint16_t)(sign | (uint32_t)lrintf(a * 16777216.0f));
+    }
+    x += ((x >> 13) & 1u) + 0xfffu;
+    return (uint16_t)(sign | ((x - 0x38000000u) >> 13));
+}
+static inline float h2f_bits(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    const uint32_t em = h & 0x7fffu;
+    float r;
+    if (em >= 0x0400u) {                         // normal (inf/nan never produced here)
+        const uint32_t x = sign | ((em << 13) + 0x38000000u);
+        std::memcpy(&r, &x, 4);
+    } else {
+        r = (float)em * (1.0f / 16777216.0f);
+        if (sign) r = -r;
+    }
+    return r;
+}
+
 template <int D>
-static int build_bimg(TcState* t, const clusters_t* host, int K) {
+static int build_bimg(TcState* t, const clusters_t* host, int K, int num_threads) {
     using C = ECfg<D>;
     const int NG = (K + C::G - 1) / C::G;
-    std::memset(t->h_bimg, 0, 2 * t->bimg_bytes);
-    for (int k = 0; k < 64; k++) t->h_ck[k] = -1e30f;
-    auto put = [&](int rank, int g, int chunk, int rowh, int elem, float v) {
-        __half h = __float2half_rn(v);
-        uint8_t* p = t->h_bimg + (size_t)rank * t->bimg_bytes + (size_t)g * C::B_GROUP + (size_t)chunk * C::NH * 16 + (size_t)rowh * 16 + elem * 2;
-        std::memcpy(p, &h, 2);
-    };
-    for (int k = 0; k < K; k++) {
+    for (int k = K; k < 64; k++) t->h_ck[k] = -1e30f;
+    int bad = 0;
+    (void)num_threads;
+#pragma omp parallel for schedule(static) num_threads(num_threads) if (num_threads > 1 && K >= 8)
+    for (int k = 0; k < NG * C::G; k++) {
+        const int g = k / C::G, cg = k % C::G;
+        // row pointer of MMA column ncol inside group g for K-chunk `chunk` (16 bytes = 8 halves)
+        auto rowp = [&](int ncol, int chunk) -> uint16_t* {
+            const int rank = ncol / C::NH, rowh = ncol % C::NH;
+            return reinterpret_cast<uint16_t*>(t->h_bimg + (size_t)rank * t->bimg_bytes + (size_t)g * C::B_GROUP +
+                                               (size_t)chunk * C::NH * 16 + (size_t)rowh * 16);
+        };
+        if (k >= K) {                                    // padding cluster of the last group: all-zero rows
+            for (int d = 0; d < D; d++)
+                for (int c = 0; c < C::NCHK; c++) std::memset(rowp(cg * D + d, c), 0, 16);
+            continue;
+        }
         double A[D][D], Gc[D][D];
         const float* Ri = host->Rinv + (size_t)k * D * D;
         for (int i = 0; i < D; i++)
             for (int j = 0; j < D; j++) { A[i][j] = 0.5 * ((double)Ri[i * D + j] + (double)Ri[j * D + i]); Gc[i][j] = 0.0; }
-        for (int j = 0; j < D; j++) {                       // Cholesky A = Gc Gc^T
+        bool ok = true;
+        for (int j = 0; j < D && ok; j++) {              // Cholesky A = Gc Gc^T
             double d = A[j][j];
             for (int p = 0; p < j; p++) d -= Gc[j][p] * Gc[j][p];
-            if (!(d > 0.0) || !std::isfinite(d)) return fail(GMM_ERR_STATE, "tensor E-step: inverse covariance of a cluster is not positive definite");
+            if (!(d > 0.0) || !std::isfinite(d)) { ok = false; break; }
             Gc[j][j] = std::sqrt(d);
             for (int i = j + 1; i < D; i++) {
                 double v = A[i][j];
@@ -795,33 +844,50 @@ static int build_bimg(TcState* t, const clusters_t* host, int K) {
                 Gc[i][j] = v / Gc[j][j];
             }
         }
-        const int g = k / C::G, cg = k % C::G;
+        if (!ok) {
+#pragma omp atomic write
+            bad = 1;
+            continue;
+        }
         for (int d = 0; d < D; d++) {
             // row d of W = Gc^T:  W[d][j] = Gc[j][d] (j >= d);  y_d = sum_j W'[d][j] z_j + v_d
             double vd = 0.0;
-            const int ncol = cg * D + d;                     // MMA column inside the group
-            const int rank = ncol / C::NH, rowh = ncol % C::NH;
-            for (int j = 0; j < D; j++) {
-                const double w = (j >= d) ? Gc[j][d] : 0.0;
-                const double wp = w * t->h_scale[j];
-                vd -= w * ((double)host->means[(size_t)k * D + j] - t->h_shift[j]);
-                const float wf = (float)wp;
-                if (!(std::fabs(wf) < 6.0e4f)) return fail(GMM_ERR_STATE, "tensor E-step: whitening factor exceeds the FP16 range");
-                const float wh = __half2float(__float2half_rn(wf));
-                const float wl = (float)(wp - (double)wh);
-                const int c = j / 8, e = j % 8;
-                put(rank, g, c, rowh, e, wh);                 // x zh
-                put(rank, g, C::CP + c, rowh, e, wh);         // x zl
-                put(rank, g, 2 * C::CP + c, rowh, e, wl);     // x zh (low part of W')
+            const int ncol = cg * D + d;
+            for (int c = 0; c < C::CP; c++) {
+                uint16_t *p1 = rowp(ncol, c), *p2 = rowp(ncol, C::CP + c), *p3 = rowp(ncol, 2 * C::CP + c);
+                for (int e = 0; e < 8; e++) {
+                    const int j = c * 8 + e;
+                    const double w = (j >= d) ? Gc[j][d] : 0.0;
+                    const double wp = w * t->h_scale[j];
+                    vd -= w * ((double)host->means[(size_t)k * D + j] - t->h_shift[j]);
+                    const float wf = (float)wp;
+                    if (!(std::fabs(wf) < 6.0e4f)) {
+#pragma omp atomic write
+                        bad = 2;
+                    }
+                    const uint16_t wh = f2h_bits(wf);
+                    const uint16_t wl = f2h_bits((float)(wp - (double)h2f_bits(wh)));
+                    p1[e] = wh;                          // x zh
+                    p2[e] = wh;                          // x zl
+                    p3[e] = wl;                          // x zh (low part of W')
+                }
             }
             const float vf = (float)vd;
-            if (!(std::fabs(vf) < 6.0e4f)) return fail(GMM_ERR_STATE, "tensor E-step: offset exceeds the FP16 range");
-            const float vh = __half2float(__float2half_rn(vf));
-            put(rank, g, 3 * C::CP, rowh, 0, vh);
-            put(rank, g, 3 * C::CP, rowh, 1, (float)(vd - (double)vh));
+            if (!(std::fabs(vf) < 6.0e4f)) {
+#pragma omp atomic write
+                bad = 2;
+            }
+            uint16_t* pv = rowp(ncol, 3 * C::CP);
+            const uint16_t vh = f2h_bits(vf);
+            std::memset(pv, 0, 16);
+            pv[0] = vh;
+            pv[1] = f2h_bits((float)(vd - (double)h2f_bits(vh)));
+            if (C::NCHK > 3 * C::CP + 1) std::memset(rowp(ncol, 3 * C::CP + 1), 0, 16);
         }
         t->h_ck[k] = host->constant[k] + logf(host->pi[k]);  // additive term of estep1 (gaussian_kernel.cu:442)
     }
+    if (bad == 1) return fail(GMM_ERR_STATE, "tensor E-step: inverse covariance of a cluster is not positive definite");
+    if (bad == 2) return fail(GMM_ERR_STATE, "tensor E-step: whitening factor exceeds the FP16 range");
     t->e_NG = NG;
     return GMM_OK;
 }
@@ -832,13 +898,17 @@ int tc_upload_params(TcState* t, const clusters_t* host, int K, cudaStream_t str
     TC_CUDA_TRY(cudaStreamSynchronize(stream));          // the pinned staging buffers may still be in flight
     int rc;
     switch (t->D) {
-        case 8: rc = build_bimg<8>(t, host, K); break;
-        case 16: rc = build_bimg<16>(t, host, K); break;
-        case 24: rc = build_bimg<24>(t, host, K); break;
+        case 8: rc = build_bimg<8>(t, host, K, t->host_threads); break;
+        case 16: rc = build_bimg<16>(t, host, K, t->host_threads); break;
+        case 24: rc = build_bimg<24>(t, host, K, t->host_threads); break;
         default: return fail(GMM_ERR_ARG, "tensor E-step: unsupported D");
     }
     if (rc) return rc;
-    TC_CUDA_TRY(cudaMemcpyAsync(t->d_bimg, t->h_bimg, 2 * t->bimg_bytes, cudaMemcpyHostToDevice, stream));
+    // only the groups in use travel (the image of each rank is contiguous per group)
+    const size_t used = (size_t)t->e_NG * (t->bimg_bytes / (size_t)(64 / (t->D == 24 ? 8 : (t->D == 16 ? 16 : 32))));
+    for (int r = 0; r < 2; r++)
+        TC_CUDA_TRY(cudaMemcpyAsync(t->d_bimg + (size_t)r * t->bimg_bytes, t->h_bimg + (size_t)r * t->bimg_bytes, used,
+                                    cudaMemcpyHostToDevice, stream));
     TC_CUDA_TRY(cudaMemcpyAsync(t->d_ck, t->h_ck, sizeof(float) * 64, cudaMemcpyHostToDevice, stream));
     return GMM_OK;
 }

