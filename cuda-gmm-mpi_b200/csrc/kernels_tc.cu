@@ -292,42 +292,34 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         // partials in the (L2-resident) per-CTA scratch, bounding the FP32 random walk to kSpill adds
         constexpr int kSpill = 16;
         double* my = scratch + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * C::MT * 128 + q * 32 + lane) * kNCL;
-        bool spilled = false;
-        for (int c = 0; c < nchunks || !spilled; c++) {
-            if (c < nchunks) {
-                const int ab = c & 1;
-                mbar_wait(&acc_full[ab], (c >> 1) & 1);
-                tc_fence_after();
+        for (int c = 0; c < nchunks; c++) {
+            const int ab = c & 1;
+            mbar_wait(&acc_full[ab], (c >> 1) & 1);
+            tc_fence_after();
 #pragma unroll
-                for (int mt = 0; mt < C::MT; mt++) {
+            for (int mt = 0; mt < C::MT; mt++) {
 #pragma unroll
-                    for (int h = 0; h < kNCL / 32; h++) {
-                        uint32_t r[32];
-                        tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + ab * (C::MT * kNCL) + mt * kNCL + h * 32, r);
-                        tmem_ld_wait();
+                for (int h = 0; h < kNCL / 32; h++) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + ab * (C::MT * kNCL) + mt * kNCL + h * 32, r);
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; j++) racc[(mt * 2 + h) * 32 + j] += __uint_as_float(r[j]);
-                    }
+                    for (int j = 0; j < 32; j++) racc[(mt * 2 + h) * 32 + j] += __uint_as_float(r[j]);
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[ab]);
             }
-            if ((c % kSpill) == kSpill - 1 || c >= nchunks - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[ab]);
+            if ((c % kSpill) == kSpill - 1 || c == nchunks - 1) {
+                // fire-and-forget double reductions (RED.ADD.F64) into this thread's private slots of the
+                // zero-initialised scratch: no load latency on the flush path
 #pragma unroll
-                for (int mt = 0; mt < C::MT; mt++) {
-                    double2* dst = reinterpret_cast<double2*>(my + (size_t)mt * 128 * kNCL);
+                for (int mt = 0; mt < C::MT; mt++)
 #pragma unroll
-                    for (int v = 0; v < kNCL / 2; v++) {
-                        double2 o = spilled ? dst[v] : make_double2(0.0, 0.0);
-                        o.x += (double)racc[mt * kNCL + 2 * v];
-                        o.y += (double)racc[mt * kNCL + 2 * v + 1];
-                        dst[v] = o;
-                        racc[mt * kNCL + 2 * v] = 0.0f;
-                        racc[mt * kNCL + 2 * v + 1] = 0.0f;
+                    for (int j = 0; j < kNCL; j++) {
+                        atomicAdd(my + (size_t)mt * 128 * kNCL + j, (double)racc[mt * kNCL + j]);
+                        racc[mt * kNCL + j] = 0.0f;
                     }
-                }
-                spilled = true;
             }
         }
     }
@@ -366,77 +358,77 @@ __global__ void mstep_tc_finalize_kernel(const double* __restrict__ scratch, int
 // through a ones column, followed by a square-and-sum epilogue, the log-sum-exp
 // over the clusters and the log-likelihood reduction.  Operands are FP16 hi/lo
 // split (z = zh + zl, W' = Wh + Wl); the K dimension concatenates
-//     [ zh | zl | zh | 1 1 0.. ]  x  [ Wh | Wh | Wl | vh vl 0.. ]
-// (the lo*lo product is dropped), FP32 accumulation in TMEM.
+//     [ zh_c zl_c ]_c | [ zh | 1 1 0.. ]     x     [ Wh_c Wh_c ]_c | [ Wl | vh vl 0.. ]
+// (the lo*lo product is dropped), FP32 accumulation in TMEM.  The duplicated Wh
+// chunk is not stored twice: the B descriptor of those MMA steps uses a leading
+// byte offset of 0, so both 8-element K chunks alias the same shared-memory chunk
+// (verified by csrc/probe/tc_probe.cu, test T5).  That makes the whole B operand
+// (all clusters: 172 KB at K=64, D=24) RESIDENT in the shared memory of one CTA;
+// only the event tiles stream.
 //
-// The whole B operand (all clusters) stays RESIDENT in shared memory: a CTA pair
-// (cta_group::2, M = 256) splits it, each CTA holding half of the N columns of
-// every cluster group, so only event tiles stream (TMA).  Per CTA, 512 threads:
-//   warp 0      TMA producer (raw [128][D] event tile, zero fill beyond n)
-//   warp 1      MMA issuer (leader CTA only): per tile NG groups x KSTEPS tcgen05.mma
+// One persistent CTA per SM, 512 threads:
+//   warp 1      MMA issuer: per 128-event tile NG groups x KSTEPS tcgen05.mma (M=128, N=G*D)
 //   warp 2      TMEM allocation
-//   warps 4-7   converters: centre/scale, FP16 hi/lo split, K-major operand image
-//   warps 8-15  epilogue (two warpgroups, even / odd cluster groups): TMEM -> registers,
-//               squares, logits, online max / sum-exp, responsibilities, log-likelihood
+//   warps 4-7   converters: coalesced loads of the event rows, centre/scale, FP16 hi/lo
+//               split, K-major SWIZZLE_NONE operand image (2 stages)
+//   warps 8-15  epilogue (two warpgroups, each takes half of the clusters of every group):
+//               tcgen05.ld -> squares -> logits -> online max / sum-exp -> responsibilities
+//               (coalesced 128-byte row segments) + log-likelihood (double)
 // ===========================================================================
 constexpr int kEThreads = 512;
 
 template <int D> struct ECfg {
     static_assert(D % 8 == 0, "tensor E-step: D must be a multiple of 8");
     static constexpr int CP = D / 8;                          // 16-byte K chunks per operand part
-    static constexpr int NCHK = (3 * CP + 1 + 1) / 2 * 2;     // K chunks (even): zh, zl, zh, ones[, pad]
-    static constexpr int KSTEPS = NCHK / 2;
+    static constexpr int NLO = (CP + 1 + 1) / 2 * 2;          // chunks of the [zh | ones (| pad)] x [Wl | v] part
+    static constexpr int NCHKA = 2 * CP + NLO;                // A image chunks: (zh_c, zl_c) pairs, then zh.., ones, pad
+    static constexpr int NCHKB = CP + NLO;                    // B image chunks: Wh_c, then Wl.., v, pad
+    static constexpr int KSTEPS = CP + NLO / 2;
     static constexpr int G = (D == 24) ? 8 : (D == 16 ? 16 : 32);   // clusters per MMA group
-    static constexpr int N = G * D;                           // MMA N (both CTAs)
-    static constexpr int NH = N / 2;                          // B rows held by each CTA per group
-    static constexpr int GH = G / 2;                          // clusters per CTA per group (B rows only)
-    static constexpr int MAXNG = 64 / G > 0 ? 64 / G : 1;     // up to 64 clusters resident
-    static constexpr int MAXGW = (MAXNG + 1) / 2;             // groups per epilogue warpgroup
-    static constexpr int A_STAGE = NCHK * 128 * 16;
-    static constexpr int B_GROUP = NCHK * NH * 16;            // bytes per group per CTA
-    static constexpr int RAWX = 128 * D * 4;
+    static constexpr int N = G * D;                           // MMA N
+    static constexpr int MAXNG = 64 / G;                      // up to 64 clusters resident
+    static constexpr int NPAIR = G / 2;                       // cluster pairs per group
+    static constexpr int PW = NPAIR / 2;                      // pairs per epilogue warpgroup per group
+    static constexpr int LPT = MAXNG * PW * 2;                // logits held per epilogue thread (= 32)
+    static constexpr int A_STAGE = NCHKA * 128 * 16;
+    static constexpr int B_GROUP = NCHKB * N * 16;
     static constexpr int OFF_B = 0;
     static constexpr int OFF_A = OFF_B + MAXNG * B_GROUP;
-    static constexpr int OFF_RAW = OFF_A + 2 * A_STAGE;
-    static constexpr int OFF_CK = OFF_RAW + 2 * RAWX;         // float[64] constant + ln(pi)
+    static constexpr int OFF_CK = OFF_A + 2 * A_STAGE;        // float[64] constant + ln(pi)
     static constexpr int OFF_EX = OFF_CK + 256;               // exchange: [2 parity][2 wg][128] x (max, sum)
     static constexpr int OFF_BAR = OFF_EX + 2 * 2 * 128 * 8;
     static constexpr int SMEM_BYTES = OFF_BAR + 512;
-    static_assert(N <= 256 && N % 32 == 0, "MMA N");
+    static_assert(N <= 256 && N % 16 == 0, "MMA N");
     static_assert(2 * N <= 512, "TMEM budget");
+    static_assert(LPT == 32, "logits per thread");
 };
 
 template <int D>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kEThreads, 1)
-estep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const uint8_t* __restrict__ b_img, const float* __restrict__ ck,
+__global__ void __launch_bounds__(kEThreads, 1)
+estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_img, const float* __restrict__ ck,
                 const float* __restrict__ shift_f, const float* __restrict__ inv_scale_f, float* __restrict__ memb,
                 size_t pitch, int n, int K, int NG, double* __restrict__ ll_out) {
     using C = ECfg<D>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-    uint64_t* raw_full = bars;          // [2]
-    uint64_t* raw_empty = bars + 2;     // [2]
-    uint64_t* a_full = bars + 4;        // [2]  (used in the leader: 8 arrivals = 4 converter warps x 2 CTAs)
-    uint64_t* a_empty = bars + 6;       // [2]  (multicast commit)
-    uint64_t* acc_full = bars + 8;      // [2]  (multicast commit)
-    uint64_t* acc_empty = bars + 10;    // [2]  (used in the leader: 8 arrivals = 4 epilogue warps x 2 CTAs)
-    uint64_t* b_full = bars + 12;       // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    uint64_t* a_full = bars;            // [2]  4 converter warps
+    uint64_t* a_empty = bars + 2;       // [2]  tcgen05.commit
+    uint64_t* acc_full = bars + 4;      // [2]  tcgen05.commit
+    uint64_t* acc_empty = bars + 6;     // [2]  8 epilogue warps
+    uint64_t* b_full = bars + 8;        // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
     float* ck_s = reinterpret_cast<float*>(smem + C::OFF_CK);
     float2* ex = reinterpret_cast<float2*>(smem + C::OFF_EX);
     float* sh_s = reinterpret_cast<float*>(smem + C::OFF_BAR + 128);   // [32] shift, [32] inverse scale
     float* isc_s = sh_s + 32;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    const int ntiles = (n + 255) / 256;
-    const int my_tiles = pair < ntiles ? (ntiles - pair + npairs - 1) / npairs : 0;
+    const int ntiles = (n + 127) / 128;
+    const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; s++) {
-            mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4);
-            mbar_init(&a_full[s], 8); mbar_init(&a_empty[s], 1);
+            mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1);
             mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8);
         }
         mbar_init(b_full, 1);
@@ -445,59 +437,53 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const uint8_t* __restr
     if (threadIdx.x < 64) ck_s[threadIdx.x] = ck[threadIdx.x];
     if (threadIdx.x < D) { sh_s[threadIdx.x] = shift_f[threadIdx.x]; isc_s[threadIdx.x] = inv_scale_f[threadIdx.x]; }
     __syncthreads();
-    if (threadIdx.x == 0) {                    // resident B: this CTA's half of every cluster group
-        const uint32_t bytes = (uint32_t)NG * C::B_GROUP;
-        mbar_arrive_expect_tx(b_full, bytes);
-        const uint8_t* src = b_img + (size_t)rank * C::MAXNG * C::B_GROUP;
-        for (int g = 0; g < NG; g++) tma_load_1d(smem + C::OFF_B + g * C::B_GROUP, src + (size_t)g * C::B_GROUP, C::B_GROUP, b_full);
+    if (threadIdx.x == 0) {                    // resident B operand: one TMA bulk copy per cluster group
+        mbar_arrive_expect_tx(b_full, (uint32_t)NG * C::B_GROUP);
+        for (int g = 0; g < NG; g++) tma_load_1d(smem + C::OFF_B + g * C::B_GROUP, b_img + (size_t)g * C::B_GROUP, C::B_GROUP, b_full);
     }
-    if (warp == 2) tmem_alloc_2cta<512>(tmem_slot);
+    if (warp == 2) tmem_alloc<512>(tmem_slot);
     mbar_wait(b_full, 0);
     tc_fence_before();
-    cluster_sync_all();
+    __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    // register re-partition (64K per SM): WG0 (TMA / MMA / alloc) 40, WG1 (converters) 72, WG2-3 (epilogue) 200
+    // register re-partition (64K per SM): WG0 (MMA / alloc) 40, WG1 (converters) 72, WG2-3 (epilogue) 200
     if (warp < 4) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-      if (warp == 0) {
-        // ===================== TMA producer =====================
+      if (warp == 1) {
+        // ===================== MMA issuer =====================
         if (elect_one()) {
-            for (int it = 0; it < my_tiles; it++) {
-                const int st = it & 1, ph = (it >> 1) & 1;
-                mbar_wait(&raw_empty[st], ph ^ 1);
-                mbar_arrive_expect_tx(&raw_full[st], C::RAWX);
-                const int e0 = (pair + it * npairs) * 256 + (int)rank * 128;
-                tma_load_2d(smem + C::OFF_RAW + st * C::RAWX, &tm_x, 0, e0, &raw_full[st]);
-            }
-        }
-      } else if (warp == 1) {
-        // ===================== MMA issuer (leader CTA) =====================
-        if (rank == 0 && elect_one()) {
-            constexpr uint32_t idesc = make_idesc_f16(256, C::N, false, false);
+            constexpr uint32_t idesc = make_idesc_f16(128, C::N, false, false);
             uint32_t nuse0 = 0, nuse1 = 0;
             for (int it = 0; it < my_tiles; it++) {
                 const int as = it & 1, aph = (it >> 1) & 1;
-                mbar_wait_cluster(&a_full[as], aph);
+                mbar_wait(&a_full[as], aph);
                 tc_fence_after();
                 const uint32_t abase = smem_u32(smem + C::OFF_A + as * C::A_STAGE);
                 for (int g = 0; g < NG; g++) {
                     const int buf = g & 1;
                     uint32_t& nuse = buf ? nuse1 : nuse0;
-                    mbar_wait_cluster(&acc_empty[buf], (nuse & 1) ^ 1);
+                    mbar_wait(&acc_empty[buf], (nuse & 1) ^ 1);
                     nuse++;
                     tc_fence_after();
                     const uint32_t bbase = smem_u32(smem + C::OFF_B + g * C::B_GROUP);
 #pragma unroll
                     for (int ks = 0; ks < C::KSTEPS; ks++) {
-                        const uint64_t adesc = make_smem_desc(abase + ks * 2 * 2048, /*LBO*/ 2048, /*SBO*/ 128);
-                        const uint64_t bdesc = make_smem_desc(bbase + ks * 2 * (C::NH * 16), /*LBO*/ C::NH * 16, /*SBO*/ 128);
-                        mma_f16_ss_2cta(tmem + buf * C::N, adesc, bdesc, idesc, ks > 0);
+                        uint64_t adesc, bdesc;
+                        if (ks < C::CP) {        // (zh_c, zl_c) x (Wh_c, Wh_c): B chunk aliased through LBO = 0
+                            adesc = make_smem_desc(abase + (2 * ks) * 2048, /*LBO*/ 2048, /*SBO*/ 128);
+                            bdesc = make_smem_desc(bbase + ks * (C::N * 16), /*LBO*/ 0, /*SBO*/ 128);
+                        } else {                 // (zh.., ones) x (Wl.., v)
+                            const int j = ks - C::CP;
+                            adesc = make_smem_desc(abase + (2 * C::CP + 2 * j) * 2048, /*LBO*/ 2048, /*SBO*/ 128);
+                            bdesc = make_smem_desc(bbase + (C::CP + 2 * j) * (C::N * 16), /*LBO*/ C::N * 16, /*SBO*/ 128);
+                        }
+                        mma_f16_ss(tmem + buf * C::N, adesc, bdesc, idesc, ks > 0);
                     }
-                    mma_commit_2cta(&acc_full[buf]);
+                    mma_commit(&acc_full[buf]);
                 }
-                mma_commit_2cta(&a_empty[as]);
+                mma_commit(&a_empty[as]);
             }
         }
       }
@@ -507,39 +493,45 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const uint8_t* __restr
         const int row = threadIdx.x - 128;
         for (int it = 0; it < my_tiles; it++) {
             const int st = it & 1, ph = (it >> 1) & 1;
-            mbar_wait(&raw_full[st], ph);
-            mbar_wait(&a_empty[st], ph ^ 1);
-            uint32_t hi[D / 2], lo[D / 2];
-            {
-                const float4* xr = reinterpret_cast<const float4*>(smem + C::OFF_RAW + st * C::RAWX + row * (D * 4));
+            const long long e = (long long)((int)blockIdx.x + it * (int)gridDim.x) * 128 + row;
+            float4 xv[D / 4];
+            if (e < n) {
+                const float4* xr = reinterpret_cast<const float4*>(x_aos + (size_t)e * D);
 #pragma unroll
-                for (int v = 0; v < D / 4; v++) {
-                    const float4 t = xr[v];
-                    const float4 s4 = reinterpret_cast<const float4*>(sh_s)[v], i4 = reinterpret_cast<const float4*>(isc_s)[v];
-                    const float z0 = (t.x - s4.x) * i4.x, z1 = (t.y - s4.y) * i4.y;
-                    const float z2 = (t.z - s4.z) * i4.z, z3 = (t.w - s4.w) * i4.w;
-                    const __half2 h01 = __floats2half2_rn(z0, z1), h23 = __floats2half2_rn(z2, z3);
-                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                    hi[2 * v] = *reinterpret_cast<const uint32_t*>(&h01);
-                    hi[2 * v + 1] = *reinterpret_cast<const uint32_t*>(&h23);
-                    lo[2 * v] = pack_half2(z0 - f01.x, z1 - f01.y);
-                    lo[2 * v + 1] = pack_half2(z2 - f23.x, z3 - f23.y);
-                }
+                for (int v = 0; v < D / 4; v++) xv[v] = __ldg(xr + v);
+            } else {
+#pragma unroll
+                for (int v = 0; v < D / 4; v++) xv[v] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            uint32_t hi[D / 2], lo[D / 2];
+#pragma unroll
+            for (int v = 0; v < D / 4; v++) {
+                const float4 t = xv[v];
+                const float4 s4 = reinterpret_cast<const float4*>(sh_s)[v], i4 = reinterpret_cast<const float4*>(isc_s)[v];
+                const float z0 = (t.x - s4.x) * i4.x, z1 = (t.y - s4.y) * i4.y;
+                const float z2 = (t.z - s4.z) * i4.z, z3 = (t.w - s4.w) * i4.w;
+                const __half2 h01 = __floats2half2_rn(z0, z1), h23 = __floats2half2_rn(z2, z3);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                hi[2 * v] = *reinterpret_cast<const uint32_t*>(&h01);
+                hi[2 * v + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                lo[2 * v] = pack_half2(z0 - f01.x, z1 - f01.y);
+                lo[2 * v + 1] = pack_half2(z2 - f23.x, z3 - f23.y);
+            }
+            mbar_wait(&a_empty[st], ph ^ 1);
             uint8_t* a = smem + C::OFF_A + st * C::A_STAGE + row * 16;     // K-major: [chunk][row][16 B]
 #pragma unroll
             for (int c = 0; c < C::CP; c++) {
                 const uint4 h = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
                 const uint4 l = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
-                *reinterpret_cast<uint4*>(a + (c) * 2048) = h;
-                *reinterpret_cast<uint4*>(a + (C::CP + c) * 2048) = l;
+                *reinterpret_cast<uint4*>(a + (2 * c) * 2048) = h;
+                *reinterpret_cast<uint4*>(a + (2 * c + 1) * 2048) = l;
                 *reinterpret_cast<uint4*>(a + (2 * C::CP + c) * 2048) = h;
             }
             *reinterpret_cast<uint4*>(a + (3 * C::CP) * 2048) = make_uint4(0x3C003C00u, 0u, 0u, 0u);      // {1, 1, 0...}
-            if (C::NCHK > 3 * C::CP + 1) *reinterpret_cast<uint4*>(a + (3 * C::CP + 1) * 2048) = make_uint4(0u, 0u, 0u, 0u);
+            if (C::NLO > C::CP + 1) *reinterpret_cast<uint4*>(a + (3 * C::CP + 1) * 2048) = make_uint4(0u, 0u, 0u, 0u);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) { mbar_arrive_cluster(&a_full[st], 0); mbar_arrive(&raw_empty[st]); }
+            if (lane == 0) mbar_arrive(&a_full[st]);
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
@@ -548,21 +540,21 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const uint8_t* __restr
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         constexpr int PC = 2 * D;                               // TMEM columns of one cluster pair
-        constexpr int NPAIR = C::G / 2;
         double ll_acc = 0.0;
-        uint32_t nfull = 0;
+        uint32_t nfull0 = 0, nfull1 = 0;
         for (int it = 0; it < my_tiles; it++) {
-            const int e = (pair + it * npairs) * 256 + (int)rank * 128 + row;
-            float lg[C::MAXGW * C::G];
+            const long long e = (long long)((int)blockIdx.x + it * (int)gridDim.x) * 128 + row;
+            float lg[C::LPT];
             float mx = -INFINITY;
 #pragma unroll
-            for (int gi = 0; gi < C::MAXGW; gi++) {
-                const int g = 2 * gi + wg;
+            for (int g = 0; g < C::MAXNG; g++) {
                 if (g < NG) {
-                    mbar_wait_cluster(&acc_full[wg], nfull & 1);
+                    const int buf = g & 1;
+                    uint32_t& nfull = buf ? nfull1 : nfull0;
+                    mbar_wait(&acc_full[buf], nfull & 1);
                     nfull++;
                     tc_fence_after();
-                    const uint32_t tcol = tmem + lane_base + wg * C::N;
+                    const uint32_t tcol = tmem + lane_base + buf * C::N + wg * (C::PW * PC);   // this warpgroup's half of the group
                     uint32_t v[2][PC];                           // ping-pong register sets, one cluster pair each
                     auto load_pair = [&](int p, uint32_t (&dst)[PC]) {
                         if constexpr (D == 24) {
@@ -577,12 +569,12 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const uint8_t* __restr
                     load_pair(0, v[0]);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int p = 0; p < NPAIR; p++) {
-                        if (p + 1 < NPAIR) load_pair(p + 1, v[(p + 1) & 1]);
-                        else {                                   // every column of this buffer has been read
+                    for (int p = 0; p < C::PW; p++) {
+                        if (p + 1 < C::PW) load_pair(p + 1, v[(p + 1) & 1]);
+                        else {                                   // every column of this warpgroup's half has been read
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive_cluster(&acc_empty[wg], 0);
+                            if (lane == 0) mbar_arrive(&acc_empty[buf]);
                         }
 #pragma unroll
                         for (int u = 0; u < 2; u++) {
@@ -593,22 +585,22 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const uint8_t* __restr
                                 const float y2 = __uint_as_float(v[p & 1][u * D + j + 2]), y3 = __uint_as_float(v[p & 1][u * D + j + 3]);
                                 s0 = fmaf(y0, y0, s0); s1 = fmaf(y1, y1, s1); s2 = fmaf(y2, y2, s2); s3 = fmaf(y3, y3, s3);
                             }
-                            const float l = fmaf(-0.5f, (s0 + s1) + (s2 + s3), ck_s[g * C::G + 2 * p + u]);
-                            lg[gi * C::G + 2 * p + u] = l;
+                            const int cg = wg * (C::PW * 2) + 2 * p + u;           // cluster inside the group
+                            const float l = fmaf(-0.5f, (s0 + s1) + (s2 + s3), ck_s[g * C::G + cg]);
+                            lg[g * (C::PW * 2) + 2 * p + u] = l;
                             mx = fmaxf(mx, l);
                         }
-                        if (p + 1 < NPAIR) tmem_ld_wait();
+                        if (p + 1 < C::PW) tmem_ld_wait();
                     }
                 } else {
 #pragma unroll
-                    for (int c = 0; c < C::G; c++) lg[gi * C::G + c] = -INFINITY;
+                    for (int c = 0; c < C::PW * 2; c++) lg[g * (C::PW * 2) + c] = -INFINITY;
                 }
             }
             // log-sum-exp over the clusters (estep2, gaussian_kernel.cu:481-503): local part, then the two warpgroups combine
             float sm = 0.f;
-            const float mref = (mx == -INFINITY) ? 0.f : mx;         // a warpgroup without any cluster group
 #pragma unroll
-            for (int j = 0; j < C::MAXGW * C::G; j++) { lg[j] = __expf(lg[j] - mref); sm += lg[j]; }
+            for (int j = 0; j < C::LPT; j++) { lg[j] = __expf(lg[j] - mx); sm += lg[j]; }
             float2* exb = ex + (it & 1) * 256;
             exb[wg * 128 + row] = make_float2(mx, sm);
             named_bar_sync(1, 256);
@@ -616,16 +608,15 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const uint8_t* __restr
             const float M = fmaxf(mx, o.x);
             const float S = sm * __expf(mx - M) + o.y * __expf(o.x - M);
             const float denom = M + logf(S);                         // :490-494
-            const float scale = __expf(mref - M) / S;                // exp(l - denom) = exp(l - mref) * exp(mref - M) / S
+            const float scale = __expf(mx - M) / S;                  // exp(l - denom) = exp(l - mx) * exp(mx - M) / S
             if (e < n) {
                 if (wg == 0) ll_acc += (double)denom;
 #pragma unroll
-                for (int gi = 0; gi < C::MAXGW; gi++) {
-                    const int g = 2 * gi + wg;
+                for (int g = 0; g < C::MAXNG; g++) {
 #pragma unroll
-                    for (int c = 0; c < C::G; c++) {
-                        const int k = g * C::G + c;
-                        if (g < NG && k < K) memb[(size_t)k * pitch + e] = lg[gi * C::G + c] * scale;   // :498-501
+                    for (int c = 0; c < C::PW * 2; c++) {
+                        const int k = g * C::G + wg * (C::PW * 2) + c;
+                        if (g < NG && k < K) memb[(size_t)k * pitch + e] = lg[g * (C::PW * 2) + c] * scale;   // :498-501
                     }
                 }
             }
@@ -640,8 +631,8 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const uint8_t* __restr
         }
     }
     tc_fence_before();
-    cluster_sync_all();
-    if (warp == 2) tmem_dealloc_2cta<512>(tmem);
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<512>(tmem);
 }
 
 // ---------------------------------------------------------------------------
@@ -663,9 +654,9 @@ struct TcState {
     // E-step
     CUtensorMap tm_x128{};
     bool emap_ok = false;
-    uint8_t* d_bimg = nullptr;       // [2 ranks][MAXNG * B_GROUP]
+    uint8_t* d_bimg = nullptr;       // [MAXNG * B_GROUP] resident B operand image
     uint8_t* h_bimg = nullptr;       // pinned
-    size_t bimg_bytes = 0;           // per rank
+    size_t bimg_bytes = 0;
     float* d_ck = nullptr;           // [64]
     float* h_ck = nullptr;           // pinned [64]
     int e_NG = 0;
@@ -726,10 +717,9 @@ int tc_create(TcState** out, const float* d_x_aos, int n, int D, int Kmax, float
     if (int rc = make_map_2d(&t->tm_g, d_memb, (uint64_t)n, (uint64_t)Kmax, (uint64_t)memb_pitch * 4, kTE, kNCL)) return rc;
     t->maps_ok = true;
     if (D == 8 || D == 16 || D == 24) {
-        if (int rc = make_map_2d(&t->tm_x128, d_x_aos, (uint64_t)D, (uint64_t)n, (uint64_t)D * 4, (uint32_t)D, 128)) return rc;
         t->bimg_bytes = bimg_bytes_for(D);
-        TC_CUDA_TRY(cudaMalloc(&t->d_bimg, 2 * t->bimg_bytes));
-        TC_CUDA_TRY(cudaMallocHost(&t->h_bimg, 2 * t->bimg_bytes));
+        TC_CUDA_TRY(cudaMalloc(&t->d_bimg, t->bimg_bytes));
+        TC_CUDA_TRY(cudaMallocHost(&t->h_bimg, t->bimg_bytes));
         TC_CUDA_TRY(cudaMalloc(&t->d_ck, sizeof(float) * 64));
         TC_CUDA_TRY(cudaMallocHost(&t->h_ck, sizeof(float) * 64));
         t->emap_ok = true;
@@ -817,15 +807,14 @@ static int build_bimg(TcState* t, const clusters_t* host, int K, int num_threads
 #pragma omp parallel for schedule(static) num_threads(num_threads) if (num_threads > 1 && K >= 8)
     for (int k = 0; k < NG * C::G; k++) {
         const int g = k / C::G, cg = k % C::G;
-        // row pointer of MMA column ncol inside group g for K-chunk `chunk` (16 bytes = 8 halves)
+        // row pointer of MMA column ncol inside group g for K-chunk `chunk` (16 bytes = 8 halves):
+        // K-major SWIZZLE_NONE image [chunk][N rows][16 B]
         auto rowp = [&](int ncol, int chunk) -> uint16_t* {
-            const int rank = ncol / C::NH, rowh = ncol % C::NH;
-            return reinterpret_cast<uint16_t*>(t->h_bimg + (size_t)rank * t->bimg_bytes + (size_t)g * C::B_GROUP +
-                                               (size_t)chunk * C::NH * 16 + (size_t)rowh * 16);
+            return reinterpret_cast<uint16_t*>(t->h_bimg + (size_t)g * C::B_GROUP + (size_t)chunk * C::N * 16 + (size_t)ncol * 16);
         };
         if (k >= K) {                                    // padding cluster of the last group: all-zero rows
             for (int d = 0; d < D; d++)
-                for (int c = 0; c < C::NCHK; c++) std::memset(rowp(cg * D + d, c), 0, 16);
+                for (int c = 0; c < C::NCHKB; c++) std::memset(rowp(cg * D + d, c), 0, 16);
             continue;
         }
         double A[D][D], Gc[D][D];
@@ -854,7 +843,7 @@ static int build_bimg(TcState* t, const clusters_t* host, int K, int num_threads
             double vd = 0.0;
             const int ncol = cg * D + d;
             for (int c = 0; c < C::CP; c++) {
-                uint16_t *p1 = rowp(ncol, c), *p2 = rowp(ncol, C::CP + c), *p3 = rowp(ncol, 2 * C::CP + c);
+                uint16_t *ph = rowp(ncol, c), *pl = rowp(ncol, C::CP + c);
                 for (int e = 0; e < 8; e++) {
                     const int j = c * 8 + e;
                     const double w = (j >= d) ? Gc[j][d] : 0.0;
@@ -866,10 +855,8 @@ static int build_bimg(TcState* t, const clusters_t* host, int K, int num_threads
                         bad = 2;
                     }
                     const uint16_t wh = f2h_bits(wf);
-                    const uint16_t wl = f2h_bits((float)(wp - (double)h2f_bits(wh)));
-                    p1[e] = wh;                          // x zh
-                    p2[e] = wh;                          // x zl
-                    p3[e] = wl;                          // x zh (low part of W')
+                    ph[e] = wh;                                                   // x (zh_c, zl_c), aliased
+                    pl[e] = f2h_bits((float)(wp - (double)h2f_bits(wh)));         // x zh_c
                 }
             }
             const float vf = (float)vd;
@@ -877,12 +864,12 @@ static int build_bimg(TcState* t, const clusters_t* host, int K, int num_threads
 #pragma omp atomic write
                 bad = 2;
             }
-            uint16_t* pv = rowp(ncol, 3 * C::CP);
+            uint16_t* pv = rowp(ncol, 2 * C::CP);
             const uint16_t vh = f2h_bits(vf);
             std::memset(pv, 0, 16);
             pv[0] = vh;
             pv[1] = f2h_bits((float)(vd - (double)h2f_bits(vh)));
-            if (C::NCHK > 3 * C::CP + 1) std::memset(rowp(ncol, 3 * C::CP + 1), 0, 16);
+            if (C::NCHKB > 2 * C::CP + 1) std::memset(rowp(ncol, 2 * C::CP + 1), 0, 16);
         }
         t->h_ck[k] = host->constant[k] + logf(host->pi[k]);  // additive term of estep1 (gaussian_kernel.cu:442)
     }
@@ -904,11 +891,9 @@ int tc_upload_params(TcState* t, const clusters_t* host, int K, cudaStream_t str
         default: return fail(GMM_ERR_ARG, "tensor E-step: unsupported D");
     }
     if (rc) return rc;
-    // only the groups in use travel (the image of each rank is contiguous per group)
+    // only the groups in use travel (the image is contiguous per group)
     const size_t used = (size_t)t->e_NG * (t->bimg_bytes / (size_t)(64 / (t->D == 24 ? 8 : (t->D == 16 ? 16 : 32))));
-    for (int r = 0; r < 2; r++)
-        TC_CUDA_TRY(cudaMemcpyAsync(t->d_bimg + (size_t)r * t->bimg_bytes, t->h_bimg + (size_t)r * t->bimg_bytes, used,
-                                    cudaMemcpyHostToDevice, stream));
+    TC_CUDA_TRY(cudaMemcpyAsync(t->d_bimg, t->h_bimg, used, cudaMemcpyHostToDevice, stream));
     TC_CUDA_TRY(cudaMemcpyAsync(t->d_ck, t->h_ck, sizeof(float) * 64, cudaMemcpyHostToDevice, stream));
     return GMM_OK;
 }
@@ -922,12 +907,12 @@ static int launch_estep_d(TcState* t, int K, double* d_ll, cudaStream_t stream) 
         TC_CUDA_TRY(cudaFuncSetAttribute(estep_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr = true;
     }
-    const int ntiles = (t->n + 255) / 256;
-    int pairs = t->num_sms / 2;
-    if (pairs > ntiles) pairs = ntiles;
-    if (pairs < 1) pairs = 1;
-    estep_tc_kernel<D><<<2 * pairs, kEThreads, C::SMEM_BYTES, stream>>>(t->tm_x128, t->d_bimg, t->d_ck, t->d_shift_f, t->d_inv_scale_f,
-                                                                        t->d_memb, t->memb_pitch, t->n, K, t->e_NG, d_ll);
+    const int ntiles = (t->n + 127) / 128;
+    int grid = t->num_sms;
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) grid = 1;
+    estep_tc_kernel<D><<<grid, kEThreads, C::SMEM_BYTES, stream>>>(t->d_x, t->d_bimg, t->d_ck, t->d_shift_f, t->d_inv_scale_f,
+                                                                   t->d_memb, t->memb_pitch, t->n, K, t->e_NG, d_ll);
     TC_CUDA_TRY(cudaGetLastError());
     return GMM_OK;
 }
@@ -959,6 +944,7 @@ static int launch_mstep_d(TcState* t, int K, double* d_stats, cudaStream_t strea
     const int gy = (K + kNCL - 1) / kNCL;
     if ((size_t)gx * gy * C::MT * 128 * kNCL > t->scratch_floats) return fail(GMM_ERR_STATE, "tensor M-step scratch too small");
     dim3 grid(gx, gy);
+    TC_CUDA_TRY(cudaMemsetAsync(t->d_scratch, 0, sizeof(double) * (size_t)gx * gy * C::MT * 128 * kNCL, stream));
     mstep_tc_kernel<D><<<grid, kMThreads, C::SMEM_BYTES, stream>>>(t->tm_x, t->tm_g, t->n, t->d_shift_f, t->d_inv_scale_f,
                                                                    t->d_scratch, per);
     TC_CUDA_TRY(cudaGetLastError());
