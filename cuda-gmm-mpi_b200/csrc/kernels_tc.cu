@@ -106,7 +106,7 @@ __device__ __forceinline__ float feature_value(const float (&z)[D], int f) {
     return 0.0f;
 }
 
-// Builds the 16-byte chunks c = P, P+8, P+16, ... of the feature vector of one event and
+// Builds the 16-byte chunks c = P, P+4, P+8, ... of the feature vector of one event and
 // stores hi/lo parts into the MN-major operand image:
 //   byte(f, e) = (f/8)*512 + (e/8)*128 + (e%8)*16 + (f%8)*2        (LBO = 128, SBO = 512)
 template <int D, int P>
@@ -114,7 +114,7 @@ __device__ __forceinline__ void build_phi_chunks(const float (&z)[D], uint8_t* h
     constexpr int NCHUNK = MCfg<D>::NCHUNK;
     const int eoff = (e >> 3) * 128 + (e & 7) * 16;
 #pragma unroll
-    for (int c = P; c < NCHUNK; c += 8) {
+    for (int c = P; c < NCHUNK; c += 4) {
         float hi[8], lo[8];
 #pragma unroll
         for (int u = 0; u < 8; u++) {
@@ -157,8 +157,8 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     // ---- one-time setup ----
     for (int i = threadIdx.x * 16; i < C::OFF_RAWX; i += kMThreads * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kNRAW; s++) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 8); }
-        for (int s = 0; s < kNST; s++) { mbar_init(&op_full[s], 8); mbar_init(&op_empty[s], 1); }
+        for (int s = 0; s < kNRAW; s++) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
+        for (int s = 0; s < kNST; s++) { mbar_init(&op_full[s], 4); mbar_init(&op_empty[s], 1); }
         for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
         fence_mbar_init();
     }
@@ -179,7 +179,7 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         if (elect_one()) {
             for (int i = 0; i < nsub; i++) {
                 const int st = i % kNRAW, ph = (i / kNRAW) & 1;
-                mbar_wait(&raw_empty[st], ph ^ 1);
+                mbar_wait_parked(&raw_empty[st], ph ^ 1, 500);
                 mbar_arrive_expect_tx(&raw_full[st], kTE * D * 4 + C::RAWG);
                 const int e0 = e_begin + i * kTE;
                 tma_load_2d(smem + C::OFF_RAWX + st * C::RAWX, &tm_x, 0, e0, &raw_full[st]);
@@ -194,8 +194,8 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 const int os = i % kNST, oph = (i / kNST) & 1;
                 const int chunk = i / kChunkSub, ab = chunk & 1;
                 const bool first = (i % kChunkSub) == 0;
-                if (first) mbar_wait(&acc_empty[ab], ((chunk >> 1) & 1) ^ 1);
-                mbar_wait(&op_full[os], oph);
+                if (first) mbar_wait_parked(&acc_empty[ab], ((chunk >> 1) & 1) ^ 1, 100);
+                mbar_wait_parked(&op_full[os], oph, 100);
                 tc_fence_after();
                 const uint32_t phi = smem_u32(smem + C::OFF_PHI + os * C::PHI_STAGE);
                 const uint32_t gam = smem_u32(smem + C::OFF_G + os * C::G_STAGE);
@@ -222,13 +222,15 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     } else if (warp < 12) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
         // ===================== operand builders =====================
-        const int part = warp - 4;                 // feature chunks c = part (mod 8)
-        const int bt = threadIdx.x - 128;          // 0..255
-        for (int i = 0; i < nsub; i++) {
+        // two builder warpgroups work on alternate sub-tiles (two sub-tiles in flight), the four warps
+        // of a group split the 16-byte feature chunks (c = part mod 4)
+        const int bwg = (warp - 4) >> 2;           // sub-tiles i = bwg (mod 2)
+        const int part = (warp - 4) & 3;
+        const int bt = threadIdx.x - 128 - bwg * 128;   // 0..127 inside the group
+        for (int i = bwg; i < nsub; i += 2) {
             const int rs = i % kNRAW, rph = (i / kNRAW) & 1;
             const int os = i % kNST, oph = (i / kNST) & 1;
-            mbar_wait(&raw_full[rs], rph);
-            mbar_wait(&op_empty[os], oph ^ 1);
+            mbar_wait_parked(&raw_full[rs], rph, 200);
             // --- features of event `lane` ---
             float z[D];
             {
@@ -243,21 +245,12 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     z[4 * v + 3] = (t.w - s4.w) * i4.w;
                 }
             }
-            uint8_t* phi_hi = smem + C::OFF_PHI + os * C::PHI_STAGE;
-            uint8_t* phi_lo = phi_hi + C::PHI_PART;
-            switch (part) {
-                case 0: build_phi_chunks<D, 0>(z, phi_hi, phi_lo, lane); break;
-                case 1: build_phi_chunks<D, 1>(z, phi_hi, phi_lo, lane); break;
-                case 2: build_phi_chunks<D, 2>(z, phi_hi, phi_lo, lane); break;
-                case 3: build_phi_chunks<D, 3>(z, phi_hi, phi_lo, lane); break;
-                case 4: build_phi_chunks<D, 4>(z, phi_hi, phi_lo, lane); break;
-                case 5: build_phi_chunks<D, 5>(z, phi_hi, phi_lo, lane); break;
-                case 6: build_phi_chunks<D, 6>(z, phi_hi, phi_lo, lane); break;
-                default: build_phi_chunks<D, 7>(z, phi_hi, phi_lo, lane); break;
-            }
-            // --- responsibilities: thread -> (cluster row k, 8-event chunk ce) ---
-            {
-                const int k = bt >> 2, ce = bt & 3;
+            // --- responsibilities: thread -> (cluster row k, 8-event chunk ce), two items per thread ---
+            uint4 gh[2], gl[2];
+#pragma unroll
+            for (int it2 = 0; it2 < 2; it2++) {
+                const int item = bt + it2 * 128;
+                const int k = item >> 2, ce = item & 3;
                 const float4* gr = reinterpret_cast<const float4*>(smem + C::OFF_RAWG + rs * C::RAWG + k * (kTE * 4) + ce * 32);
                 const float4 a = gr[0], b = gr[1];
                 float g[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -268,13 +261,28 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     hi[u] = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
                     lo[u] = v - hi[u];
                 }
-                uint4 h, l;
-                h.x = pack_half2(hi[0], hi[1]); h.y = pack_half2(hi[2], hi[3]); h.z = pack_half2(hi[4], hi[5]); h.w = pack_half2(hi[6], hi[7]);
-                l.x = pack_half2(lo[0], lo[1]); l.y = pack_half2(lo[2], lo[3]); l.z = pack_half2(lo[4], lo[5]); l.w = pack_half2(lo[6], lo[7]);
+                gh[it2] = make_uint4(pack_half2(hi[0], hi[1]), pack_half2(hi[2], hi[3]), pack_half2(hi[4], hi[5]), pack_half2(hi[6], hi[7]));
+                gl[it2] = make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]), pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7]));
+            }
+            mbar_wait_parked(&op_empty[os], oph ^ 1, 200);
+            uint8_t* phi_hi = smem + C::OFF_PHI + os * C::PHI_STAGE;
+            uint8_t* phi_lo = phi_hi + C::PHI_PART;
+            switch (part) {
+                case 0: build_phi_chunks<D, 0>(z, phi_hi, phi_lo, lane); break;
+                case 1: build_phi_chunks<D, 1>(z, phi_hi, phi_lo, lane); break;
+                case 2: build_phi_chunks<D, 2>(z, phi_hi, phi_lo, lane); break;
+                default: build_phi_chunks<D, 3>(z, phi_hi, phi_lo, lane); break;
+            }
+            {
                 // K-major B image: byte(k, e) = (e/8)*1024 + k*16 + (e%8)*2      (LBO = 1024, SBO = 128)
                 uint8_t* g_hi = smem + C::OFF_G + os * C::G_STAGE;
-                *reinterpret_cast<uint4*>(g_hi + ce * 1024 + k * 16) = h;
-                *reinterpret_cast<uint4*>(g_hi + C::G_PART + ce * 1024 + k * 16) = l;
+#pragma unroll
+                for (int it2 = 0; it2 < 2; it2++) {
+                    const int item = bt + it2 * 128;
+                    const int k = item >> 2, ce = item & 3;
+                    *reinterpret_cast<uint4*>(g_hi + ce * 1024 + k * 16) = gh[it2];
+                    *reinterpret_cast<uint4*>(g_hi + C::G_PART + ce * 1024 + k * 16) = gl[it2];
+                }
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -294,7 +302,7 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         double* my = scratch + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * C::MT * 128 + q * 32 + lane) * kNCL;
         for (int c = 0; c < nchunks; c++) {
             const int ab = c & 1;
-            mbar_wait(&acc_full[ab], (c >> 1) & 1);
+            mbar_wait_parked(&acc_full[ab], (c >> 1) & 1, 500);
             tc_fence_after();
 #pragma unroll
             for (int mt = 0; mt < C::MT; mt++) {
@@ -458,13 +466,13 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
             uint32_t nuse0 = 0, nuse1 = 0;
             for (int it = 0; it < my_tiles; it++) {
                 const int as = it & 1, aph = (it >> 1) & 1;
-                mbar_wait(&a_full[as], aph);
+                mbar_wait_parked(&a_full[as], aph, 200);
                 tc_fence_after();
                 const uint32_t abase = smem_u32(smem + C::OFF_A + as * C::A_STAGE);
                 for (int g = 0; g < NG; g++) {
                     const int buf = g & 1;
                     uint32_t& nuse = buf ? nuse1 : nuse0;
-                    mbar_wait(&acc_empty[buf], (nuse & 1) ^ 1);
+                    mbar_wait_parked(&acc_empty[buf], (nuse & 1) ^ 1, 100);
                     nuse++;
                     tc_fence_after();
                     const uint32_t bbase = smem_u32(smem + C::OFF_B + g * C::B_GROUP);
@@ -517,7 +525,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                 lo[2 * v] = pack_half2(z0 - f01.x, z1 - f01.y);
                 lo[2 * v + 1] = pack_half2(z2 - f23.x, z3 - f23.y);
             }
-            mbar_wait(&a_empty[st], ph ^ 1);
+            mbar_wait_parked(&a_empty[st], ph ^ 1, 1000);
             uint8_t* a = smem + C::OFF_A + st * C::A_STAGE + row * 16;     // K-major: [chunk][row][16 B]
 #pragma unroll
             for (int c = 0; c < C::CP; c++) {
@@ -551,11 +559,15 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                 if (g < NG) {
                     const int buf = g & 1;
                     uint32_t& nfull = buf ? nfull1 : nfull0;
-                    mbar_wait(&acc_full[buf], nfull & 1);
+                    mbar_wait_parked(&acc_full[buf], nfull & 1, 200);
                     nfull++;
                     tc_fence_after();
                     const uint32_t tcol = tmem + lane_base + buf * C::N + wg * (C::PW * PC);   // this warpgroup's half of the group
-                    uint32_t v[2][PC];                           // ping-pong register sets, one cluster pair each
+                    // all TMEM loads of this warpgroup's half are issued back to back (batches of two cluster
+                    // pairs = 4*D registers), ONE wait per batch, and the buffer is handed back to the MMA issuer
+                    // before the arithmetic: the accumulator round trip, not the math, bounds the kernel
+                    constexpr int BATCH = (C::PW >= 2) ? 2 : 1;                  // cluster pairs per batch
+                    static_assert(C::PW % BATCH == 0, "pairs per warpgroup");
                     auto load_pair = [&](int p, uint32_t (&dst)[PC]) {
                         if constexpr (D == 24) {
                             tmem_ld_32x32(tcol + p * PC, *reinterpret_cast<uint32_t(*)[32]>(&dst[0]));
@@ -566,31 +578,35 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                             tmem_ld_32x16(tcol + p * PC, *reinterpret_cast<uint32_t(*)[16]>(&dst[0]));
                         }
                     };
-                    load_pair(0, v[0]);
-                    tmem_ld_wait();
 #pragma unroll
-                    for (int p = 0; p < C::PW; p++) {
-                        if (p + 1 < C::PW) load_pair(p + 1, v[(p + 1) & 1]);
-                        else {                                   // every column of this warpgroup's half has been read
+                    for (int p0 = 0; p0 < C::PW; p0 += BATCH) {
+                        uint32_t v[BATCH][PC];
+#pragma unroll
+                        for (int b = 0; b < BATCH; b++) load_pair(p0 + b, v[b]);
+                        tmem_ld_wait();
+                        if (p0 + BATCH >= C::PW) {               // every column of this warpgroup's half has been read
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&acc_empty[buf]);
                         }
 #pragma unroll
-                        for (int u = 0; u < 2; u++) {
-                            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                        for (int b = 0; b < BATCH; b++) {
+                            const int p = p0 + b;
 #pragma unroll
-                            for (int j = 0; j < D; j += 4) {
-                                const float y0 = __uint_as_float(v[p & 1][u * D + j]), y1 = __uint_as_float(v[p & 1][u * D + j + 1]);
-                                const float y2 = __uint_as_float(v[p & 1][u * D + j + 2]), y3 = __uint_as_float(v[p & 1][u * D + j + 3]);
-                                s0 = fmaf(y0, y0, s0); s1 = fmaf(y1, y1, s1); s2 = fmaf(y2, y2, s2); s3 = fmaf(y3, y3, s3);
+                            for (int u = 0; u < 2; u++) {
+                                uint64_t a01 = 0ull, a23 = 0ull;                    // two packed FP32 pairs (FFMA2)
+#pragma unroll
+                                for (int j = 0; j < D; j += 4) {
+                                    sq_acc2(a01, v[b][u * D + j], v[b][u * D + j + 1]);
+                                    sq_acc2(a23, v[b][u * D + j + 2], v[b][u * D + j + 3]);
+                                }
+                                const float qsum = hsum2(a01, a23);
+                                const int cg = wg * (C::PW * 2) + 2 * p + u;           // cluster inside the group
+                                const float l = fmaf(-0.5f, qsum, ck_s[g * C::G + cg]);
+                                lg[g * (C::PW * 2) + 2 * p + u] = l;
+                                mx = fmaxf(mx, l);
                             }
-                            const int cg = wg * (C::PW * 2) + 2 * p + u;           // cluster inside the group
-                            const float l = fmaf(-0.5f, (s0 + s1) + (s2 + s3), ck_s[g * C::G + cg]);
-                            lg[g * (C::PW * 2) + 2 * p + u] = l;
-                            mx = fmaxf(mx, l);
                         }
-                        if (p + 1 < C::PW) tmem_ld_wait();
                     }
                 } else {
 #pragma unroll
@@ -611,12 +627,17 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
             const float scale = __expf(mx - M) / S;                  // exp(l - denom) = exp(l - mx) * exp(mx - M) / S
             if (e < n) {
                 if (wg == 0) ll_acc += (double)denom;
+                float* gp = memb + (size_t)(wg * (C::PW * 2)) * pitch + e;      // row of this warpgroup's first cluster
 #pragma unroll
                 for (int g = 0; g < C::MAXNG; g++) {
+                    const int kbase = g * C::G + wg * (C::PW * 2);
+                    if (kbase < K) {
+                        float* gq = gp + (size_t)(g * C::G) * pitch;
 #pragma unroll
-                    for (int c = 0; c < C::PW * 2; c++) {
-                        const int k = g * C::G + wg * (C::PW * 2) + c;
-                        if (g < NG && k < K) memb[(size_t)k * pitch + e] = lg[g * (C::PW * 2) + c] * scale;   // :498-501
+                        for (int c = 0; c < C::PW * 2; c++) {
+                            if (kbase + c < K) *gq = lg[g * (C::PW * 2) + c] * scale;   // :498-501
+                            gq += pitch;
+                        }
                     }
                 }
             }

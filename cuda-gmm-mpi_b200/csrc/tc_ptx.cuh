@@ -38,6 +38,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// Same, but lets the hardware park the thread for up to `ns` nanoseconds per probe: a waiting
+// warp then issues far fewer TRYWAIT/BRA pairs and leaves the issue slots to the warps that work.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+    }
+}
+// packed FP32 pair: acc.xy += y.xy * y.xy   (SASS: FFMA2)
+__device__ __forceinline__ void sq_acc2(uint64_t& acc, uint32_t y_lo, uint32_t y_hi) {
+    uint64_t y;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "r"(y_lo), "r"(y_hi));
+    asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(acc) : "l"(y));
+}
+__device__ __forceinline__ float hsum2(uint64_t a, uint64_t b) {   // (a.x + a.y) + (b.x + b.y)
+    uint64_t s;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(s) : "l"(a), "l"(b));
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(s));
+    return lo + hi;
+}
 
 // ---- proxy fences -----------------------------------------------------------
 // Generic-proxy shared-memory writes -> visible to the async proxy (TMA, tcgen05.mma operands).
