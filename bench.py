@@ -172,20 +172,21 @@ def main():
     del ev_all
     path = {"auto": pkg.PATH_AUTO, "simt": pkg.PATH_SIMT, "tensor": pkg.PATH_TENSOR}[args.path]
 
-    uid = None
-    if world > 1:
+    def fresh_nccl_id():
+        """A ncclUniqueId can bootstrap ONE communicator: every engine gets its own (rank 0 draws it,
+        torch.distributed broadcasts the 128 bytes)."""
         buf = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
             buf = torch.frombuffer(bytearray(pkg.nccl_unique_id()), dtype=torch.uint8).clone()
         dist.broadcast(buf, src=0)
-        uid = bytes(buf.numpy().tobytes())
+        return bytes(buf.numpy().tobytes())
 
     def make_engine():
         eng = pkg.Engine(None, K, device=local_rank, n_global=N, offset=begin,
                          events_ptr=ev_pinned.data_ptr(), n_local=count, D=D)
         eng.set_option("path", path)
         if world > 1:
-            eng.comm_init(world, rank, uid)
+            eng.comm_init(world, rank, fresh_nccl_id())
         return eng
 
     def barrier():

@@ -264,6 +264,9 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 gh[it2] = make_uint4(pack_half2(hi[0], hi[1]), pack_half2(hi[2], hi[3]), pack_half2(hi[4], hi[5]), pack_half2(hi[6], hi[7]));
                 gl[it2] = make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]), pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7]));
             }
+            // the raw tiles are in registers now: hand the stage back to the TMA producer before the long part
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&raw_empty[rs]);
             mbar_wait_parked(&op_empty[os], oph ^ 1, 200);
             uint8_t* phi_hi = smem + C::OFF_PHI + os * C::PHI_STAGE;
             uint8_t* phi_lo = phi_hi + C::PHI_PART;
@@ -286,7 +289,7 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&op_full[os]); mbar_arrive(&raw_empty[rs]); }
+            if (lane == 0) mbar_arrive(&op_full[os]);
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
@@ -383,7 +386,8 @@ __global__ void mstep_tc_finalize_kernel(const double* __restrict__ scratch, int
 //               tcgen05.ld -> squares -> logits -> online max / sum-exp -> responsibilities
 //               (coalesced 128-byte row segments) + log-likelihood (double)
 // ===========================================================================
-constexpr int kEThreads = 512;
+constexpr int kEWG = 4;                      // epilogue warpgroups (TMEM -> register latency is hidden by warps, not by ILP)
+constexpr int kEThreads = 256 + 128 * kEWG;
 
 template <int D> struct ECfg {
     static_assert(D % 8 == 0, "tensor E-step: D must be a multiple of 8");
@@ -392,23 +396,25 @@ template <int D> struct ECfg {
     static constexpr int NCHKA = 2 * CP + NLO;                // A image chunks: (zh_c, zl_c) pairs, then zh.., ones, pad
     static constexpr int NCHKB = CP + NLO;                    // B image chunks: Wh_c, then Wl.., v, pad
     static constexpr int KSTEPS = CP + NLO / 2;
-    static constexpr int G = (D == 24) ? 8 : (D == 16 ? 16 : 32);   // clusters per MMA group
+    static constexpr int G = (D == 24) ? 8 : (D == 16 ? 16 : 32);   // clusters per MMA group (N = 192 / 256 / 256)
     static constexpr int N = G * D;                           // MMA N
     static constexpr int MAXNG = 64 / G;                      // up to 64 clusters resident
     static constexpr int NPAIR = G / 2;                       // cluster pairs per group
-    static constexpr int PW = NPAIR / 2;                      // pairs per epilogue warpgroup per group
-    static constexpr int LPT = MAXNG * PW * 2;                // logits held per epilogue thread (= 32)
+    static constexpr int PW = NPAIR / kEWG;                   // pairs per epilogue warpgroup per group
+    static constexpr int LPT = MAXNG * PW * 2;                // logits held per epilogue thread
     static constexpr int A_STAGE = NCHKA * 128 * 16;
     static constexpr int B_GROUP = NCHKB * N * 16;
     static constexpr int OFF_B = 0;
     static constexpr int OFF_A = OFF_B + MAXNG * B_GROUP;
     static constexpr int OFF_CK = OFF_A + 2 * A_STAGE;        // float[64] constant + ln(pi)
-    static constexpr int OFF_EX = OFF_CK + 256;               // exchange: [2 parity][2 wg][128] x (max, sum)
-    static constexpr int OFF_BAR = OFF_EX + 2 * 2 * 128 * 8;
+    static constexpr int OFF_EX = OFF_CK + 256;               // exchange: [2 parity][kEWG][128] x (max, sum)
+    static constexpr int OFF_BAR = OFF_EX + 2 * kEWG * 128 * 8;
     static constexpr int SMEM_BYTES = OFF_BAR + 512;
     static_assert(N <= 256 && N % 16 == 0, "MMA N");
-    static_assert(2 * N <= 512, "TMEM budget");
-    static_assert(LPT == 32, "logits per thread");
+    static_assert(NPAIR % kEWG == 0, "cluster pairs per group must split over the epilogue warpgroups");
+    static constexpr int NBUF = 512 / N;                      // TMEM accumulator buffers (2; N = 96 with 5 buffers measured slower)
+    static_assert(NBUF * N <= 512 && NBUF >= 2, "TMEM budget");
+    static_assert(LPT * kEWG == 64, "logits per thread");
 };
 
 template <int D>
@@ -421,10 +427,10 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
     uint64_t* a_full = bars;            // [2]  4 converter warps
     uint64_t* a_empty = bars + 2;       // [2]  tcgen05.commit
-    uint64_t* acc_full = bars + 4;      // [2]  tcgen05.commit
-    uint64_t* acc_empty = bars + 6;     // [2]  8 epilogue warps
-    uint64_t* b_full = bars + 8;        // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    uint64_t* b_full = bars + 4;        // [1]
+    uint64_t* acc_full = bars + 5;      // [NBUF]  tcgen05.commit
+    uint64_t* acc_empty = bars + 5 + C::NBUF;     // [NBUF]  8 epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * C::NBUF);
     float* ck_s = reinterpret_cast<float*>(smem + C::OFF_CK);
     float2* ex = reinterpret_cast<float2*>(smem + C::OFF_EX);
     float* sh_s = reinterpret_cast<float*>(smem + C::OFF_BAR + 128);   // [32] shift, [32] inverse scale
@@ -435,10 +441,8 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
     const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 2; s++) {
-            mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1);
-            mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8);
-        }
+        for (int s = 0; s < 2; s++) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < C::NBUF; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4 * kEWG); }
         mbar_init(b_full, 1);
         fence_mbar_init();
     }
@@ -456,24 +460,24 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    // register re-partition (64K per SM): WG0 (MMA / alloc) 40, WG1 (converters) 72, WG2-3 (epilogue) 200
+    // register re-partition INSIDE the CTA's launch allocation (768 threads x 80 registers = 61440):
+    // WG0 (MMA / alloc) 24, WG1 (converters) 72, four epilogue warpgroups 88 each = 57344
+    static_assert((24 + 72 + 88 * kEWG) * 128 <= kEThreads * 80, "setmaxnreg budget exceeds the CTA's register allocation");
     if (warp < 4) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
       if (warp == 1) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(128, C::N, false, false);
-            uint32_t nuse0 = 0, nuse1 = 0;
+            uint32_t gi = 0;                                   // running group index: buffer = gi % NBUF
             for (int it = 0; it < my_tiles; it++) {
                 const int as = it & 1, aph = (it >> 1) & 1;
                 mbar_wait_parked(&a_full[as], aph, 200);
                 tc_fence_after();
                 const uint32_t abase = smem_u32(smem + C::OFF_A + as * C::A_STAGE);
-                for (int g = 0; g < NG; g++) {
-                    const int buf = g & 1;
-                    uint32_t& nuse = buf ? nuse1 : nuse0;
-                    mbar_wait_parked(&acc_empty[buf], (nuse & 1) ^ 1, 100);
-                    nuse++;
+                for (int g = 0; g < NG; g++, gi++) {
+                    const uint32_t buf = gi % C::NBUF, use = gi / C::NBUF;
+                    mbar_wait_parked(&acc_empty[buf], (use & 1) ^ 1, 100);
                     tc_fence_after();
                     const uint32_t bbase = smem_u32(smem + C::OFF_B + g * C::B_GROUP);
 #pragma unroll
@@ -542,14 +546,14 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
             if (lane == 0) mbar_arrive(&a_full[st]);
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
         // ===================== epilogue =====================
         const int wg = (warp - 8) >> 2, q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         constexpr int PC = 2 * D;                               // TMEM columns of one cluster pair
         double ll_acc = 0.0;
-        uint32_t nfull0 = 0, nfull1 = 0;
+        uint32_t gi = 0;                                       // running group index, as in the MMA issuer
         for (int it = 0; it < my_tiles; it++) {
             const long long e = (long long)((int)blockIdx.x + it * (int)gridDim.x) * 128 + row;
             float lg[C::LPT];
@@ -557,10 +561,9 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
 #pragma unroll
             for (int g = 0; g < C::MAXNG; g++) {
                 if (g < NG) {
-                    const int buf = g & 1;
-                    uint32_t& nfull = buf ? nfull1 : nfull0;
-                    mbar_wait_parked(&acc_full[buf], nfull & 1, 200);
-                    nfull++;
+                    const uint32_t buf = gi % C::NBUF, use = gi / C::NBUF;
+                    gi++;
+                    mbar_wait_parked(&acc_full[buf], use & 1, 200);
                     tc_fence_after();
                     const uint32_t tcol = tmem + lane_base + buf * C::N + wg * (C::PW * PC);   // this warpgroup's half of the group
                     // all TMEM loads of this warpgroup's half are issued back to back (batches of two cluster
@@ -617,12 +620,15 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
             float sm = 0.f;
 #pragma unroll
             for (int j = 0; j < C::LPT; j++) { lg[j] = __expf(lg[j] - mx); sm += lg[j]; }
-            float2* exb = ex + (it & 1) * 256;
+            float2* exb = ex + (it & 1) * (kEWG * 128);
             exb[wg * 128 + row] = make_float2(mx, sm);
-            named_bar_sync(1, 256);
-            const float2 o = exb[(wg ^ 1) * 128 + row];
-            const float M = fmaxf(mx, o.x);
-            const float S = sm * __expf(mx - M) + o.y * __expf(o.x - M);
+            named_bar_sync(1, 128 * kEWG);
+            float M = mx;
+#pragma unroll
+            for (int w = 0; w < kEWG; w++) M = fmaxf(M, exb[w * 128 + row].x);
+            float S = 0.f;
+#pragma unroll
+            for (int w = 0; w < kEWG; w++) { const float2 o = exb[w * 128 + row]; S += o.y * __expf(o.x - M); }
             const float denom = M + logf(S);                         // :490-494
             const float scale = __expf(mx - M) / S;                  // exp(l - denom) = exp(l - mx) * exp(mx - M) / S
             if (e < n) {

@@ -349,10 +349,18 @@ def test_cli_two_gpus_equals_one(loaded, tmp_path):
     ev = pkg.synth.make_blobs(20_001, 4, 4, seed=2)
     data = tmp_path / "d.bin"
     pkg.synth.write_bin(str(data), ev)
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_oracle import _parse_summary
     outs = {}
     for g in (1, 2):
         env = dict(os.environ, GMM_ITERS="10", GMM_GPUS=str(g))
         r = subprocess.run([exe, "4", str(data), str(tmp_path / f"o{g}"), "4"], capture_output=True, text=True, env=env, timeout=600)
         assert r.returncode == 0, r.stdout + r.stderr
-        outs[g] = open(tmp_path / f"o{g}.summary").read()
-    assert outs[1] == outs[2]
+        outs[g] = _parse_summary(str(tmp_path / f"o{g}.summary"))
+    assert len(outs[1]) == len(outs[2]) == 4
+    for a, b in zip(outs[1], outs[2]):          # only the summation order differs between the two runs
+        assert abs(a["N"] - b["N"]) <= 1e-4 * a["N"]
+        assert abs(a["pi"] - b["pi"]) <= 2e-6
+        np.testing.assert_allclose(a["means"], b["means"], atol=1.1e-3)
+        np.testing.assert_allclose(np.array(a["R"]), np.array(b["R"]), atol=1.1e-3)
