@@ -198,7 +198,7 @@ static int upload_params(gmm_ctx* c, int K) {
 template <int D>
 static void launch_estep_simt_d(gmm_ctx* c, int K) {
     const int blocks = (c->n + kEstepThreads - 1) / kEstepThreads;
-    estep_simt_kernel<D><<<blocks, kEstepThreads, 0, c->stream>>>(c->d_x_soa, c->n, K, c->d_epack, c->d_memb, c->memb_pitch,
+    estep_simt_kernel<D><<<blocks, kEstepThreads, 0, c->stream>>>(c->d_x_soa, c->memb_pitch, c->n, K, c->d_epack, c->d_memb, c->memb_pitch,
                                                                  c->d_stats + (size_t)K * c->F);
 }
 static int launch_estep_simt(gmm_ctx* c, int K) {
@@ -232,7 +232,7 @@ static int launch_mstep_simt_t(gmm_ctx* c, int K) {
     if (per < kMstepTE) per = kMstepTE;
     gx = (c->n + per - 1) / per;
     dim3 grid(gx, (K + KT - 1) / KT);
-    mstep_simt_kernel<JMAX, CPT><<<grid, kMstepThreads, smem, c->stream>>>(c->d_x_soa, c->n, c->D, K, c->d_memb, c->memb_pitch,
+    mstep_simt_kernel<JMAX, CPT><<<grid, kMstepThreads, smem, c->stream>>>(c->d_x_soa, c->memb_pitch, c->n, c->D, K, c->d_memb, c->memb_pitch,
                                                                            c->d_shift, c->d_stats, per);
     CUDA_TRY(cudaGetLastError());
     return GMM_OK;
@@ -317,7 +317,7 @@ static int ensure_moments(gmm_ctx* c) {
     CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(double) * 2 * D, c->stream));
     if (c->n > 0) {
         dim3 grid(std::min(4 * c->num_sms, (c->n + 255) / 256), D);
-        column_moments_kernel<<<grid, 256, 0, c->stream>>>(c->d_x_soa, c->n, D, c->d_stats);
+        column_moments_kernel<<<grid, 256, 0, c->stream>>>(c->d_x_soa, c->memb_pitch, c->n, D, c->d_stats);
         CUDA_TRY(cudaGetLastError());
     }
     if (c->nranks > 1) {
@@ -394,8 +394,8 @@ int gmm_create(gmm_ctx** out, int device, int n_local, int D, int Kmax, const fl
     CREATE_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     const size_t nmax = n_local > 0 ? (size_t)n_local : 1;
     CREATE_TRY(cudaMalloc(&c->d_x_aos, sizeof(float) * nmax * D));
-    CREATE_TRY(cudaMalloc(&c->d_x_soa, sizeof(float) * nmax * D));
-    c->memb_pitch = (nmax + 31) / 32 * 32;
+    c->memb_pitch = (nmax + 31) / 32 * 32;         // also the row pitch of the SoA event copy
+    CREATE_TRY(cudaMalloc(&c->d_x_soa, sizeof(float) * c->memb_pitch * D));
     CREATE_TRY(cudaMalloc(&c->d_memb, sizeof(float) * c->memb_pitch * Kmax));
     CREATE_TRY(cudaMalloc(&c->d_epack, sizeof(float) * (size_t)Kmax * epack_stride(D)));
     CREATE_TRY(cudaMallocHost(&c->h_epack, sizeof(float) * (size_t)Kmax * epack_stride(D)));
@@ -406,11 +406,11 @@ int gmm_create(gmm_ctx** out, int device, int n_local, int D, int Kmax, const fl
     if (n_local > 0) {
         CREATE_TRY(cudaMemcpyAsync(c->d_x_aos, events_aos, sizeof(float) * (size_t)n_local * D, cudaMemcpyHostToDevice, c->stream));
         dim3 blk(32, 8);
-        transpose_aos_to_soa_kernel<<<(n_local + 31) / 32, blk, 0, c->stream>>>(c->d_x_aos, c->d_x_soa, n_local, D);
+        transpose_aos_to_soa_kernel<<<(n_local + 31) / 32, blk, 0, c->stream>>>(c->d_x_aos, c->d_x_soa, c->memb_pitch, n_local, D);
         CREATE_TRY(cudaGetLastError());
     }
     {
-        int rc = tc_create(&c->tc, c->d_x_aos, n_local, D, Kmax, c->d_memb, c->memb_pitch, c->num_sms, c->stream);
+        int rc = tc_create(&c->tc, c->d_x_aos, c->d_x_soa, n_local, D, Kmax, c->d_memb, c->memb_pitch, c->num_sms, c->stream);
         if (rc) { gmm_destroy(c); return rc; }
         tc_set_host_threads(c->tc, c->host_threads);
     }

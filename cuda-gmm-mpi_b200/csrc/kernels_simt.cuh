@@ -4,7 +4,7 @@
 // as estep1 forms it ((x - mu) first, then the D x D form), FP64 accumulation
 // of the M-step statistics.  They are the accuracy anchor on the device and the
 // path for shapes the tcgen05 kernels do not cover.  Layouts:
-//   xs    : events SoA  [D][n]   (device transpose of the AoS shard; the
+//   xs    : events SoA  [D][xpitch] (device transpose of the AoS shard, rows pitched to 32 events; the
 //           reference keeps the same copy: gaussian.cu:209-218, 373-377)
 //   memb  : responsibilities, cluster-major [K][n] (gaussian.h:75)
 //   stats : per cluster F = 1 + D + D(D+1)/2 doubles
@@ -39,7 +39,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ---------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(kEstepThreads)
-estep_simt_kernel(const float* __restrict__ xs, int n, int K, const float* __restrict__ epack,
+estep_simt_kernel(const float* __restrict__ xs, size_t xpitch, int n, int K, const float* __restrict__ epack,
                   float* __restrict__ memb, size_t pitch, double* __restrict__ ll_out) {
     constexpr int STRIDE = epack_stride_c(D);
     constexpr int COEF = (D + 3) & ~3;
@@ -51,7 +51,7 @@ estep_simt_kernel(const float* __restrict__ xs, int n, int K, const float* __res
     const bool valid = e < n;
     float x[D];
 #pragma unroll
-    for (int d = 0; d < D; d++) x[d] = valid ? xs[(size_t)d * n + e] : 0.0f;
+    for (int d = 0; d < D; d++) x[d] = valid ? xs[(size_t)d * xpitch + e] : 0.0f;
 
     float run_max = -INFINITY, run_sum = 0.0f;
     for (int k0 = 0; k0 < K; k0 += kEstepClusterChunk) {
@@ -119,7 +119,7 @@ constexpr int kMstepTE = 32;
 
 template <int JMAX, int CPT>
 __global__ void __launch_bounds__(kMstepThreads, 1)
-mstep_simt_kernel(const float* __restrict__ xs, int n, int D, int K, const float* __restrict__ memb, size_t pitch,
+mstep_simt_kernel(const float* __restrict__ xs, size_t xpitch, int n, int D, int K, const float* __restrict__ memb, size_t pitch,
                   const double* __restrict__ shift, double* __restrict__ stats, int events_per_block) {
     constexpr int FP = 16 * JMAX;          // padded feature count
     constexpr int KT = 16 * CPT;           // clusters per block
@@ -160,7 +160,7 @@ mstep_simt_kernel(const float* __restrict__ xs, int n, int D, int K, const float
         for (int idx = tid; idx < kMstepTE * D; idx += kMstepThreads) {       // shifted events
             const int d = idx / kMstepTE, t = idx % kMstepTE;
             const long long e = e0 + t;
-            xt[t * GMM_MAX_DIMENSIONS + d] = (e < eend) ? (double)xs[(size_t)d * n + e] - shift[d] : 0.0;
+            xt[t * GMM_MAX_DIMENSIONS + d] = (e < eend) ? (double)xs[(size_t)d * xpitch + e] - shift[d] : 0.0;
         }
         for (int idx = tid; idx < kMstepTE * KT; idx += kMstepThreads) {      // responsibilities
             const int kk = idx / kMstepTE, t = idx % kMstepTE;
@@ -207,7 +207,7 @@ mstep_simt_kernel(const float* __restrict__ xs, int n, int D, int K, const float
 }
 
 // AoS [n][D] -> SoA [D][n] (gaussian.cu:212-218 done on the device).
-__global__ void transpose_aos_to_soa_kernel(const float* __restrict__ aos, float* __restrict__ soa, int n, int D) {
+__global__ void transpose_aos_to_soa_kernel(const float* __restrict__ aos, float* __restrict__ soa, size_t xpitch, int n, int D) {
     __shared__ float tile[32][33];
     const int e0 = blockIdx.x * 32;
     for (int d0 = 0; d0 < D; d0 += 32) {
@@ -219,7 +219,7 @@ __global__ void transpose_aos_to_soa_kernel(const float* __restrict__ aos, float
         __syncthreads();
         for (int r = threadIdx.y; r < 32; r += blockDim.y) {
             const int d = d0 + r, e = e0 + threadIdx.x;
-            if (d < D && e < n) soa[(size_t)d * n + e] = tile[threadIdx.x][r];
+            if (d < D && e < n) soa[(size_t)d * xpitch + e] = tile[threadIdx.x][r];
         }
         __syncthreads();
     }
@@ -228,9 +228,9 @@ __global__ void transpose_aos_to_soa_kernel(const float* __restrict__ aos, float
 // Column sums for seeding: out[d] += sum x, out[D+d] += sum x^2 (double).
 // Replaces mvtmeans / averageVariance (gaussian_kernel.cu:54-102), which scan
 // the events serially with one thread per dimension.
-__global__ void column_moments_kernel(const float* __restrict__ xs, int n, int D, double* __restrict__ out) {
+__global__ void column_moments_kernel(const float* __restrict__ xs, size_t xpitch, int n, int D, double* __restrict__ out) {
     const int d = blockIdx.y;
-    const float* col = xs + (size_t)d * n;
+    const float* col = xs + (size_t)d * xpitch;
     double s1 = 0, s2 = 0;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         const double v = col[e];

@@ -52,11 +52,17 @@ using namespace ptx;
 // ---------------------------------------------------------------------------
 // M-step kernel configuration
 // ---------------------------------------------------------------------------
+#ifndef GMM_CHUNKSUB
+#define GMM_CHUNKSUB 4
+#endif
+#ifndef GMM_SPILL
+#define GMM_SPILL 16
+#endif
 constexpr int kTE = 32;          // events per sub-tile (MMA K extent per operand part)
 constexpr int kNCL = 64;         // clusters per CTA pass (MMA N)
 constexpr int kNST = 3;          // operand stages
 constexpr int kNRAW = 4;         // raw (TMA) stages
-constexpr int kChunkSub = 4;     // sub-tiles between TMEM flushes (128 events: 24 MMA steps per accumulator chain)
+constexpr int kChunkSub = GMM_CHUNKSUB;     // sub-tiles between TMEM flushes
 constexpr int kMThreads = 512;
 constexpr float kGammaScale = 1024.0f;   // responsibilities are scaled by 2^10 before the FP16 split
 
@@ -68,7 +74,7 @@ template <int D> struct MCfg {
     static constexpr int PHI_STAGE = 2 * PHI_PART;
     static constexpr int G_PART = kNCL * kTE * 2;
     static constexpr int G_STAGE = 2 * G_PART;
-    static constexpr int RAWX = (kTE * D * 4 + 127) & ~127;
+    static constexpr int RAWX = D * kTE * 4;              // [D][32 events] from the SoA copy
     static constexpr int RAWG = kNCL * kTE * 4;
     static constexpr int OFF_PHI = 0;
     static constexpr int OFF_G = OFF_PHI + kNST * PHI_STAGE;
@@ -77,6 +83,7 @@ template <int D> struct MCfg {
     static constexpr int OFF_BAR = OFF_RAWG + kNRAW * RAWG;
     static constexpr int SMEM_BYTES = OFF_BAR + 512;
     static constexpr int TMEM_COLS = 2 * MT * kNCL;       // two accumulator buffers
+    static_assert(OFF_RAWG % 1024 == 0 && RAWG % 1024 == 0, "SWIZZLE_128B TMA destinations need 1024-byte alignment");
 };
 
 __host__ __device__ constexpr int tri_row(int t) {        // t = i(i+1)/2 + j, j <= i  ->  i
@@ -182,7 +189,7 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 mbar_wait_parked(&raw_empty[st], ph ^ 1, 500);
                 mbar_arrive_expect_tx(&raw_full[st], kTE * D * 4 + C::RAWG);
                 const int e0 = e_begin + i * kTE;
-                tma_load_2d(smem + C::OFF_RAWX + st * C::RAWX, &tm_x, 0, e0, &raw_full[st]);
+                tma_load_2d(smem + C::OFF_RAWX + st * C::RAWX, &tm_x, e0, 0, &raw_full[st]);
                 tma_load_2d(smem + C::OFF_RAWG + st * C::RAWG, &tm_g, e0, k0, &raw_full[st]);
             }
         }
@@ -206,7 +213,7 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     const uint32_t pb = gam + (seg == 2 ? C::G_PART : 0);
 #pragma unroll
                     for (int ks = 0; ks < kTE / 16; ks++) {
-                        const uint64_t bdesc = make_smem_desc(pb + ks * 2048, /*LBO*/ 1024, /*SBO*/ 128);
+                        const uint64_t bdesc = make_smem_desc(pb + ks * 256, /*LBO*/ 128, /*SBO*/ 512);
 #pragma unroll
                         for (int mt = 0; mt < C::MT; mt++) {
                             const uint64_t adesc = make_smem_desc(pa + mt * 8192 + ks * 256, /*LBO*/ 128, /*SBO*/ 512);
@@ -234,25 +241,30 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             // --- features of event `lane` ---
             float z[D];
             {
-                const float4* xr = reinterpret_cast<const float4*>(smem + C::OFF_RAWX + rs * C::RAWX + lane * (D * 4));
+                const float* xr = reinterpret_cast<const float*>(smem + C::OFF_RAWX + rs * C::RAWX) + lane;   // [d][32]: conflict-free
 #pragma unroll
                 for (int v = 0; v < D / 4; v++) {
-                    const float4 t = xr[v];
                     const float4 s4 = reinterpret_cast<const float4*>(sh_s)[v], i4 = reinterpret_cast<const float4*>(isc_s)[v];
-                    z[4 * v + 0] = (t.x - s4.x) * i4.x;
-                    z[4 * v + 1] = (t.y - s4.y) * i4.y;
-                    z[4 * v + 2] = (t.z - s4.z) * i4.z;
-                    z[4 * v + 3] = (t.w - s4.w) * i4.w;
+                    z[4 * v + 0] = (xr[(4 * v + 0) * kTE] - s4.x) * i4.x;
+                    z[4 * v + 1] = (xr[(4 * v + 1) * kTE] - s4.y) * i4.y;
+                    z[4 * v + 2] = (xr[(4 * v + 2) * kTE] - s4.z) * i4.z;
+                    z[4 * v + 3] = (xr[(4 * v + 3) * kTE] - s4.w) * i4.w;
                 }
             }
-            // --- responsibilities: thread -> (cluster row k, 8-event chunk ce), two items per thread ---
+            // --- responsibilities: thread -> (cluster row k, 8-event chunk ce), two items per thread.
+            // The raw tile is written by TMA with SWIZZLE_128B (16-byte chunk c of row r sits at chunk
+            // c ^ (r & 7)), so 8 lanes reading the same chunk of 8 consecutive rows hit 8 different
+            // bank groups; the operand image puts the 4 K-chunks of an 8-row group next to each other
+            // (LBO = 128, SBO = 512), so a warp stores 512 contiguous bytes: no bank conflicts either way.
             uint4 gh[2], gl[2];
 #pragma unroll
             for (int it2 = 0; it2 < 2; it2++) {
                 const int item = bt + it2 * 128;
-                const int k = item >> 2, ce = item & 3;
-                const float4* gr = reinterpret_cast<const float4*>(smem + C::OFF_RAWG + rs * C::RAWG + k * (kTE * 4) + ce * 32);
-                const float4 a = gr[0], b = gr[1];
+                const int kg = item >> 5, l = item & 31;
+                const int k = kg * 8 + (l & 7), ce = l >> 3;
+                const uint8_t* grow = smem + C::OFF_RAWG + rs * C::RAWG + k * (kTE * 4);
+                const float4 a = *reinterpret_cast<const float4*>(grow + (((2 * ce) ^ (k & 7)) << 4));
+                const float4 b = *reinterpret_cast<const float4*>(grow + (((2 * ce + 1) ^ (k & 7)) << 4));
                 float g[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
                 float hi[8], lo[8];
 #pragma unroll
@@ -277,14 +289,14 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 default: build_phi_chunks<D, 3>(z, phi_hi, phi_lo, lane); break;
             }
             {
-                // K-major B image: byte(k, e) = (e/8)*1024 + k*16 + (e%8)*2      (LBO = 1024, SBO = 128)
+                // K-major B image: byte(k, e) = (k/8)*512 + (e/8)*128 + (k%8)*16 + (e%8)*2      (LBO = 128, SBO = 512)
                 uint8_t* g_hi = smem + C::OFF_G + os * C::G_STAGE;
 #pragma unroll
                 for (int it2 = 0; it2 < 2; it2++) {
                     const int item = bt + it2 * 128;
-                    const int k = item >> 2, ce = item & 3;
-                    *reinterpret_cast<uint4*>(g_hi + ce * 1024 + k * 16) = gh[it2];
-                    *reinterpret_cast<uint4*>(g_hi + C::G_PART + ce * 1024 + k * 16) = gl[it2];
+                    const int kg = item >> 5, l = item & 31;
+                    *reinterpret_cast<uint4*>(g_hi + kg * 512 + l * 16) = gh[it2];
+                    *reinterpret_cast<uint4*>(g_hi + C::G_PART + kg * 512 + l * 16) = gl[it2];
                 }
             }
             fence_proxy_async_smem();
@@ -301,7 +313,7 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         for (int j = 0; j < C::MT * kNCL; j++) racc[j] = 0.0f;
         // second level: every kSpill chunks the FP32 partial sums move into this thread's double
         // partials in the (L2-resident) per-CTA scratch, bounding the FP32 random walk to kSpill adds
-        constexpr int kSpill = 16;
+        constexpr int kSpill = GMM_SPILL;
         double* my = scratch + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * C::MT * 128 + q * 32 + lane) * kNCL;
         for (int c = 0; c < nchunks; c++) {
             const int ab = c & 1;
@@ -386,7 +398,7 @@ __global__ void mstep_tc_finalize_kernel(const double* __restrict__ scratch, int
 //               tcgen05.ld -> squares -> logits -> online max / sum-exp -> responsibilities
 //               (coalesced 128-byte row segments) + log-likelihood (double)
 // ===========================================================================
-constexpr int kEWG = 4;                      // epilogue warpgroups (TMEM -> register latency is hidden by warps, not by ILP)
+constexpr int kEWG = 2;                      // epilogue warpgroups (2: 1.97 ms at C3; 4 warpgroups of 88 registers: 2.07 ms)
 constexpr int kEThreads = 256 + 128 * kEWG;
 
 template <int D> struct ECfg {
@@ -460,11 +472,14 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    // register re-partition INSIDE the CTA's launch allocation (768 threads x 80 registers = 61440):
-    // WG0 (MMA / alloc) 24, WG1 (converters) 72, four epilogue warpgroups 88 each = 57344
-    static_assert((24 + 72 + 88 * kEWG) * 128 <= kEThreads * 80, "setmaxnreg budget exceeds the CTA's register allocation");
+    // register re-partition INSIDE the CTA's launch allocation (setmaxnreg.inc blocks forever beyond it):
+    //   2 epilogue warpgroups: 512 threads x 128 = 65536 -> WG0 40, converters 72, epilogue 200 each
+    //   4 epilogue warpgroups: 768 threads x  80 = 61440 -> WG0 24, converters 72, epilogue  88 each
+    constexpr int kRegWG0 = (kEWG == 2) ? 40 : 24, kRegEpi = (kEWG == 2) ? 200 : 88;
+    static_assert((kRegWG0 + 72 + kRegEpi * kEWG) * 128 <= kEThreads * ((kEWG == 2) ? 128 : 80),
+                  "setmaxnreg budget exceeds the CTA's register allocation");
     if (warp < 4) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegWG0));
       if (warp == 1) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
@@ -546,7 +561,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
             if (lane == 0) mbar_arrive(&a_full[st]);
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegEpi));
         // ===================== epilogue =====================
         const int wg = (warp - 8) >> 2, q = warp & 3;
         const int row = q * 32 + lane;
@@ -704,7 +719,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
     return fn;
 }
 
-static int make_map_2d(CUtensorMap* m, const void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes, uint32_t box0, uint32_t box1) {
+static int make_map_2d(CUtensorMap* m, const void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes, uint32_t box0, uint32_t box1,
+                       bool swizzle128 = false) {
     auto fn = encode_fn();
     if (!fn) return fail(GMM_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t dims[2] = {dim0, dim1};
@@ -712,7 +728,7 @@ static int make_map_2d(CUtensorMap* m, const void* base, uint64_t dim0, uint64_t
     cuuint32_t box[2] = {box0, box1};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(GMM_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     return GMM_OK;
@@ -729,7 +745,7 @@ static size_t bimg_bytes_for(int D) {
     switch (D) { case 8: return ecfg_bimg_bytes<8>(); case 16: return ecfg_bimg_bytes<16>(); case 24: return ecfg_bimg_bytes<24>(); default: return 0; }
 }
 
-int tc_create(TcState** out, const float* d_x_aos, int n, int D, int Kmax, float* d_memb, size_t memb_pitch, int num_sms,
+int tc_create(TcState** out, const float* d_x_aos, const float* d_x_soa, int n, int D, int Kmax, float* d_memb, size_t memb_pitch, int num_sms,
               cudaStream_t stream) {
     (void)stream;
     TcState* t = new TcState();
@@ -739,9 +755,10 @@ int tc_create(TcState** out, const float* d_x_aos, int n, int D, int Kmax, float
     TC_CUDA_TRY(cudaMalloc(&t->d_shift_f, sizeof(float) * GMM_MAX_DIMENSIONS));
     TC_CUDA_TRY(cudaMalloc(&t->d_inv_scale_f, sizeof(float) * GMM_MAX_DIMENSIONS));
     TC_CUDA_TRY(cudaMalloc(&t->d_scale, sizeof(double) * GMM_MAX_DIMENSIONS));
-    // tensor maps: events [n][D] (dim0 = D), responsibilities [Kmax][pitch] viewed as (events, clusters)
-    if (int rc = make_map_2d(&t->tm_x, d_x_aos, (uint64_t)D, (uint64_t)n, (uint64_t)D * 4, (uint32_t)D, kTE)) return rc;
-    if (int rc = make_map_2d(&t->tm_g, d_memb, (uint64_t)n, (uint64_t)Kmax, (uint64_t)memb_pitch * 4, kTE, kNCL)) return rc;
+    // tensor maps: SoA events [D][pitch] viewed as (events, dims) -> smem tile [D][32 events];
+    // responsibilities [Kmax][pitch] viewed as (events, clusters)
+    if (int rc = make_map_2d(&t->tm_x, d_x_soa, (uint64_t)n, (uint64_t)D, (uint64_t)memb_pitch * 4, kTE, (uint32_t)D)) return rc;
+    if (int rc = make_map_2d(&t->tm_g, d_memb, (uint64_t)n, (uint64_t)Kmax, (uint64_t)memb_pitch * 4, kTE, kNCL, /*swizzle128=*/true)) return rc;
     t->maps_ok = true;
     if (D == 8 || D == 16 || D == 24) {
         t->bimg_bytes = bimg_bytes_for(D);

@@ -12,8 +12,8 @@ struct TcState;
 bool tc_mstep_supported(int D, int K);
 bool tc_estep_supported(int D, int K);
 
-// memb_pitch: row pitch (in floats) of the cluster-major responsibilities buffer.
-int  tc_create(TcState** out, const float* d_x_aos, int n, int D, int Kmax, float* d_memb, size_t memb_pitch,
+// memb_pitch: row pitch (in floats) of the cluster-major responsibilities buffer AND of the SoA event copy.
+int  tc_create(TcState** out, const float* d_x_aos, const float* d_x_soa, int n, int D, int Kmax, float* d_memb, size_t memb_pitch,
                int num_sms, cudaStream_t stream);
 void tc_destroy(TcState*);
 void tc_set_host_threads(TcState*, int n);

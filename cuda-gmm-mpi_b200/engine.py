@@ -32,7 +32,8 @@ class GmmError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, "libgmm_b200.so")
+    # GMM_B200_LIB: development override (kernel variants for experiments); the product is libgmm_b200.so
+    return os.environ.get("GMM_B200_LIB") or os.path.join(_HERE, "libgmm_b200.so")
 
 
 def build_library(force=False):
