@@ -420,6 +420,23 @@ int gmm_create(gmm_ctx** out, int device, int n_local, int D, int Kmax, const fl
     return GMM_OK;
 }
 
+// Replace the events of this shard (same n_local, D): H2D copy + device transpose.  The global
+// moments (shift / scale, seeding statistics) are recomputed on the next collective call.
+int gmm_upload_events(gmm_ctx* c, const float* events_aos) {
+    if (!c || (c->n > 0 && !events_aos)) return fail(GMM_ERR_ARG, "gmm_upload_events: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->n > 0) {
+        CUDA_TRY(cudaMemcpyAsync(c->d_x_aos, events_aos, sizeof(float) * (size_t)c->n * c->D, cudaMemcpyHostToDevice, c->stream));
+        dim3 blk(32, 8);
+        transpose_aos_to_soa_kernel<<<(c->n + 31) / 32, blk, 0, c->stream>>>(c->d_x_aos, c->d_x_soa, c->memb_pitch, c->n, c->D);
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->have_shift = false;
+    c->memb_valid = false;
+    return GMM_OK;
+}
+
 void gmm_destroy(gmm_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);

@@ -56,6 +56,7 @@ def load_library():
     L.gmm_version.restype = C.c_char_p
     L.gmm_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                              C.c_longlong, C.c_longlong]
+    L.gmm_upload_events.argtypes = [C.c_void_p, C.c_void_p]
     L.gmm_destroy.argtypes = [C.c_void_p]
     L.gmm_destroy.restype = None
     L.gmm_shard_range.argtypes = [C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
@@ -206,6 +207,13 @@ class Engine:
 
     def __exit__(self, *a):
         self.close()
+
+    def upload_events(self, events=None, events_ptr=None):
+        if events is not None:
+            events = np.ascontiguousarray(events, np.float32)
+            assert events.shape == (self.n, self.D)
+            events_ptr = events.ctypes.data
+        _check(self.lib.gmm_upload_events(self.h, events_ptr))
 
     def new_clusters(self, with_memberships=False):
         return Clusters(self.Kmax, self.D, self.n if with_memberships else 0)

@@ -79,6 +79,10 @@ int  gmm_create(gmm_ctx** out, int device, int n_local, int D, int Kmax,
                 const float* events_aos, long long n_global, long long offset);
 void gmm_destroy(gmm_ctx*);
 
+/* Replace the events of this shard in an existing context (same n_local and D): the H2D copy
+ * of gaussian.cu:370 without re-creating buffers or the communicator.                        */
+int  gmm_upload_events(gmm_ctx*, const float* events_aos);
+
 /* Contiguous event range of shard `rank` of `nranks` (gaussian.cu:348-352,
  * with quirk Q6 fixed: the remainder goes to the LAST shard).              */
 void gmm_shard_range(long long n_global, int nranks, int rank,

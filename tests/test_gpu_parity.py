@@ -280,6 +280,26 @@ def test_full_size_properties_config2(loaded, path):
     np.testing.assert_allclose(got.pi.sum(), 1.0, rtol=1e-5)
 
 
+def test_upload_events_equals_fresh_context(loaded):
+    """gmm_upload_events replaces the shard in place: same results as a new context."""
+    pkg = loaded
+    ev = pkg.synth.make_blobs(30_000, 16, 6, seed=31)
+    K = 6
+    with pkg.Engine(ev, K) as eng:
+        eng.seed(K)
+        ll_a, _ = eng.em(K, 4, 4)
+        a = eng.get_clusters(K)
+    with pkg.Engine(np.zeros_like(ev), K) as eng:
+        eng.seed(K)                                   # moments of the placeholder data must not survive
+        eng.upload_events(ev)
+        eng.seed(K)
+        ll_b, _ = eng.em(K, 4, 4)
+        b = eng.get_clusters(K)
+    assert ll_a == ll_b
+    for f in ("N", "means", "R", "Rinv", "constant", "pi"):
+        np.testing.assert_array_equal(getattr(a, f), getattr(b, f))
+
+
 def test_reference_binary_matches_oracle_and_engine(loaded, oracle64, tmp_path):
     """The UNMODIFIED reference program (oracle/_ref/gaussianMPI_ref), run here on
     the GPU, against the oracle and the engine: pins the oracle to the reference."""
