@@ -24,34 +24,38 @@ const char* last_error_cstr() { return g_err.c_str(); }
 // Doolittle factorisation A = L U (unit L), then A^-1 column by column.
 // ---------------------------------------------------------------------------
 template <class T>
-void lu_inverse_nopivot(T* a, int n, T* logabsdet, T* work) {
+void lu_inverse_nopivot(T* __restrict__ a, int n, T* logabsdet, T* __restrict__ w) {
+    // Elimination applied to [A | I]: every inner loop is an axpy over a contiguous row (vectorises
+    // without reassociation).  Forward pass leaves U in the upper triangle of `a` and L^-1 in `w`;
+    // the backward pass turns `w` into U^-1 L^-1 = A^-1.
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) w[i * n + j] = (i == j) ? T(1) : T(0);
     T ld = 0;
     for (int k = 0; k < n; k++) {
         const T piv = a[k * n + k];
         ld += std::log(std::fabs(piv));
         const T rp = T(1) / piv;
+        const T* ak = a + k * n;
+        const T* wk = w + k * n;
         for (int i = k + 1; i < n; i++) {
             const T l = a[i * n + k] * rp;
-            a[i * n + k] = l;
-            for (int j = k + 1; j < n; j++) a[i * n + j] -= l * a[k * n + j];
+            T* ai = a + i * n;
+            T* wi = w + i * n;
+            for (int j = k + 1; j < n; j++) ai[j] -= l * ak[j];
+            for (int j = 0; j <= k; j++) wi[j] -= l * wk[j];
         }
     }
-    // Solve L U X = I.  work holds X column-major-by-construction, copied back row-major.
-    for (int c = 0; c < n; c++) {
-        T* x = work + c * n;                      // column c of the inverse
-        for (int i = 0; i < n; i++) {             // forward: L y = e_c
-            T s = (i == c) ? T(1) : T(0);
-            for (int k = (c < i ? c : i); k < i; k++) s -= a[i * n + k] * x[k];
-            x[i] = (i < c) ? T(0) : s;
+    for (int k = n - 1; k >= 0; k--) {
+        T* wk = w + k * n;
+        for (int j = k + 1; j < n; j++) {
+            const T u = a[k * n + j];
+            const T* wj = w + j * n;
+            for (int c = 0; c < n; c++) wk[c] -= u * wj[c];
         }
-        for (int i = n - 1; i >= 0; i--) {        // backward: U x = y
-            T s = x[i];
-            for (int k = i + 1; k < n; k++) s -= a[i * n + k] * x[k];
-            x[i] = s / a[i * n + i];
-        }
+        const T rp = T(1) / a[k * n + k];
+        for (int c = 0; c < n; c++) wk[c] *= rp;
     }
-    for (int i = 0; i < n; i++)
-        for (int j = 0; j < n; j++) a[i * n + j] = work[j * n + i];
+    for (int i = 0; i < n * n; i++) a[i] = w[i];
     *logabsdet = ld;
 }
 template void lu_inverse_nopivot<float>(float*, int, float*, float*);

@@ -26,6 +26,9 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
+#if defined(__F16C__) && defined(__AVX__)
+#include <immintrin.h>
+#endif
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -398,42 +401,41 @@ __global__ void mstep_tc_finalize_kernel(const double* __restrict__ scratch, int
 //               tcgen05.ld -> squares -> logits -> online max / sum-exp -> responsibilities
 //               (coalesced 128-byte row segments) + log-likelihood (double)
 // ===========================================================================
-constexpr int kEWG = 2;                      // epilogue warpgroups (2: 1.97 ms at C3; 4 warpgroups of 88 registers: 2.07 ms)
-constexpr int kEThreads = 256 + 128 * kEWG;
+constexpr int kEThreads = 512;
 
+// Block structure.  W is upper triangular, so the 8 output columns d in [8c, 8c+8) of a cluster
+// ("block" c) only need the K chunks z_j with j >= c.  Columns are therefore grouped by block:
+// one MMA N tile = block c of 16 clusters (N = 128), and block c issues only the k-steps it needs —
+// 5 + 4 + 2 = 11 instead of 15 at D = 24 (-27 % tensor work and TMEM accumulator traffic).
 template <int D> struct ECfg {
     static_assert(D % 8 == 0, "tensor E-step: D must be a multiple of 8");
-    static constexpr int CP = D / 8;                          // 16-byte K chunks per operand part
+    static constexpr int CP = D / 8;                          // 8-wide chunks of z / blocks of output columns
     static constexpr int NLO = (CP + 1 + 1) / 2 * 2;          // chunks of the [zh | ones (| pad)] x [Wl | v] part
     static constexpr int NCHKA = 2 * CP + NLO;                // A image chunks: (zh_c, zl_c) pairs, then zh.., ones, pad
     static constexpr int NCHKB = CP + NLO;                    // B image chunks: Wh_c, then Wl.., v, pad
-    static constexpr int KSTEPS = CP + NLO / 2;
-    static constexpr int G = (D == 24) ? 8 : (D == 16 ? 16 : 32);   // clusters per MMA group (N = 192 / 256 / 256)
-    static constexpr int N = G * D;                           // MMA N
-    static constexpr int MAXNG = 64 / G;                      // up to 64 clusters resident
-    static constexpr int NPAIR = G / 2;                       // cluster pairs per group
-    static constexpr int PW = NPAIR / kEWG;                   // pairs per epilogue warpgroup per group
-    static constexpr int LPT = MAXNG * PW * 2;                // logits held per epilogue thread
+    static constexpr int GB = 16;                             // clusters per supergroup
+    static constexpr int N = GB * 8;                          // MMA N = one block of a supergroup (128 columns)
+    static constexpr int MAXSG = 64 / GB;                     // up to 64 clusters resident
+    static constexpr int NBUF = 512 / N;                      // TMEM accumulator buffers (4)
+    static constexpr int CW = GB / 2;                         // clusters per epilogue warpgroup per supergroup
+    static constexpr int LPT = MAXSG * CW;                    // logits held per epilogue thread (= 32)
     static constexpr int A_STAGE = NCHKA * 128 * 16;
-    static constexpr int B_GROUP = NCHKB * N * 16;
+    static constexpr int B_BLOCK = NCHKB * N * 16;            // one block of one supergroup
+    static constexpr int B_SG = CP * B_BLOCK;
     static constexpr int OFF_B = 0;
-    static constexpr int OFF_A = OFF_B + MAXNG * B_GROUP;
+    static constexpr int OFF_A = OFF_B + MAXSG * B_SG;
     static constexpr int OFF_CK = OFF_A + 2 * A_STAGE;        // float[64] constant + ln(pi)
-    static constexpr int OFF_EX = OFF_CK + 256;               // exchange: [2 parity][kEWG][128] x (max, sum)
-    static constexpr int OFF_BAR = OFF_EX + 2 * kEWG * 128 * 8;
+    static constexpr int OFF_EX = OFF_CK + 256;               // exchange: [2 parity][2 wg][128] x (max, sum)
+    static constexpr int OFF_BAR = OFF_EX + 2 * 2 * 128 * 8;
     static constexpr int SMEM_BYTES = OFF_BAR + 512;
-    static_assert(N <= 256 && N % 16 == 0, "MMA N");
-    static_assert(NPAIR % kEWG == 0, "cluster pairs per group must split over the epilogue warpgroups");
-    static constexpr int NBUF = 512 / N;                      // TMEM accumulator buffers (2; N = 96 with 5 buffers measured slower)
-    static_assert(NBUF * N <= 512 && NBUF >= 2, "TMEM budget");
-    static_assert(LPT * kEWG == 64, "logits per thread");
+    static_assert(LPT == 32, "logits per thread");
 };
 
 template <int D>
 __global__ void __launch_bounds__(kEThreads, 1)
 estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_img, const float* __restrict__ ck,
                 const float* __restrict__ shift_f, const float* __restrict__ inv_scale_f, float* __restrict__ memb,
-                size_t pitch, int n, int K, int NG, double* __restrict__ ll_out) {
+                size_t pitch, int n, int K, int NSG, double* __restrict__ ll_out) {
     using C = ECfg<D>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -454,16 +456,16 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; s++) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < C::NBUF; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4 * kEWG); }
+        for (int s = 0; s < C::NBUF; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
         mbar_init(b_full, 1);
         fence_mbar_init();
     }
     if (threadIdx.x < 64) ck_s[threadIdx.x] = ck[threadIdx.x];
     if (threadIdx.x < D) { sh_s[threadIdx.x] = shift_f[threadIdx.x]; isc_s[threadIdx.x] = inv_scale_f[threadIdx.x]; }
     __syncthreads();
-    if (threadIdx.x == 0) {                    // resident B operand: one TMA bulk copy per cluster group
-        mbar_arrive_expect_tx(b_full, (uint32_t)NG * C::B_GROUP);
-        for (int g = 0; g < NG; g++) tma_load_1d(smem + C::OFF_B + g * C::B_GROUP, b_img + (size_t)g * C::B_GROUP, C::B_GROUP, b_full);
+    if (threadIdx.x == 0) {                    // resident B operand: one TMA bulk copy per block
+        mbar_arrive_expect_tx(b_full, (uint32_t)NSG * C::B_SG);
+        for (int g = 0; g < NSG * C::CP; g++) tma_load_1d(smem + C::OFF_B + g * C::B_BLOCK, b_img + (size_t)g * C::B_BLOCK, C::B_BLOCK, b_full);
     }
     if (warp == 2) tmem_alloc<512>(tmem_slot);
     mbar_wait(b_full, 0);
@@ -472,43 +474,45 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    // register re-partition INSIDE the CTA's launch allocation (setmaxnreg.inc blocks forever beyond it):
-    //   2 epilogue warpgroups: 512 threads x 128 = 65536 -> WG0 40, converters 72, epilogue 200 each
-    //   4 epilogue warpgroups: 768 threads x  80 = 61440 -> WG0 24, converters 72, epilogue  88 each
-    constexpr int kRegWG0 = (kEWG == 2) ? 40 : 24, kRegEpi = (kEWG == 2) ? 200 : 88;
-    static_assert((kRegWG0 + 72 + kRegEpi * kEWG) * 128 <= kEThreads * ((kEWG == 2) ? 128 : 80),
-                  "setmaxnreg budget exceeds the CTA's register allocation");
+    // register re-partition inside the CTA's launch allocation (512 x 128): WG0 40, converters 72, epilogue 2 x 200
     if (warp < 4) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegWG0));
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
       if (warp == 1) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(128, C::N, false, false);
-            uint32_t gi = 0;                                   // running group index: buffer = gi % NBUF
+            uint32_t bi = 0;                                   // running block index: buffer = bi % NBUF
             for (int it = 0; it < my_tiles; it++) {
                 const int as = it & 1, aph = (it >> 1) & 1;
                 mbar_wait_parked(&a_full[as], aph, 200);
                 tc_fence_after();
                 const uint32_t abase = smem_u32(smem + C::OFF_A + as * C::A_STAGE);
-                for (int g = 0; g < NG; g++, gi++) {
-                    const uint32_t buf = gi % C::NBUF, use = gi / C::NBUF;
-                    mbar_wait_parked(&acc_empty[buf], (use & 1) ^ 1, 100);
-                    tc_fence_after();
-                    const uint32_t bbase = smem_u32(smem + C::OFF_B + g * C::B_GROUP);
+                for (int sg = 0; sg < NSG; sg++) {
 #pragma unroll
-                    for (int ks = 0; ks < C::KSTEPS; ks++) {
-                        uint64_t adesc, bdesc;
-                        if (ks < C::CP) {        // (zh_c, zl_c) x (Wh_c, Wh_c): B chunk aliased through LBO = 0
-                            adesc = make_smem_desc(abase + (2 * ks) * 2048, /*LBO*/ 2048, /*SBO*/ 128);
-                            bdesc = make_smem_desc(bbase + ks * (C::N * 16), /*LBO*/ 0, /*SBO*/ 128);
-                        } else {                 // (zh.., ones) x (Wl.., v)
-                            const int j = ks - C::CP;
-                            adesc = make_smem_desc(abase + (2 * C::CP + 2 * j) * 2048, /*LBO*/ 2048, /*SBO*/ 128);
-                            bdesc = make_smem_desc(bbase + (C::CP + 2 * j) * (C::N * 16), /*LBO*/ C::N * 16, /*SBO*/ 128);
+                    for (int c = 0; c < C::CP; c++, bi++) {
+                        const uint32_t buf = bi % C::NBUF, use = bi / C::NBUF;
+                        mbar_wait_parked(&acc_empty[buf], (use & 1) ^ 1, 100);
+                        tc_fence_after();
+                        const uint32_t bbase = smem_u32(smem + C::OFF_B + (sg * C::CP + c) * C::B_BLOCK);
+                        bool acc = false;
+#pragma unroll
+                        for (int j = c; j < C::CP; j++) {       // (zh_j, zl_j) x (Wh_j, Wh_j): B chunk aliased through LBO = 0
+                            const uint64_t adesc = make_smem_desc(abase + (2 * j) * 2048, /*LBO*/ 2048, /*SBO*/ 128);
+                            const uint64_t bdesc = make_smem_desc(bbase + j * (C::N * 16), /*LBO*/ 0, /*SBO*/ 128);
+                            mma_f16_ss(tmem + buf * C::N, adesc, bdesc, idesc, acc);
+                            acc = true;
                         }
-                        mma_f16_ss(tmem + buf * C::N, adesc, bdesc, idesc, ks > 0);
+#pragma unroll
+                        for (int t = 0; t < C::NLO / 2; t++) {  // (zh.., ones) x (Wl.., v): needed iff it holds a chunk index >= c
+                            if (2 * t + 1 >= c) {
+                                const uint64_t adesc = make_smem_desc(abase + (2 * C::CP + 2 * t) * 2048, /*LBO*/ 2048, /*SBO*/ 128);
+                                const uint64_t bdesc = make_smem_desc(bbase + (C::CP + 2 * t) * (C::N * 16), /*LBO*/ C::N * 16, /*SBO*/ 128);
+                                mma_f16_ss(tmem + buf * C::N, adesc, bdesc, idesc, acc);
+                                acc = true;
+                            }
+                        }
+                        mma_commit(&acc_full[buf]);
                     }
-                    mma_commit(&acc_full[buf]);
                 }
                 mma_commit(&a_empty[as]);
             }
@@ -561,102 +565,79 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
             if (lane == 0) mbar_arrive(&a_full[st]);
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegEpi));
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
         // ===================== epilogue =====================
         const int wg = (warp - 8) >> 2, q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        constexpr int PC = 2 * D;                               // TMEM columns of one cluster pair
         double ll_acc = 0.0;
-        uint32_t gi = 0;                                       // running group index, as in the MMA issuer
+        uint32_t bi = 0;                                       // running block index, as in the MMA issuer
         for (int it = 0; it < my_tiles; it++) {
             const long long e = (long long)((int)blockIdx.x + it * (int)gridDim.x) * 128 + row;
             float lg[C::LPT];
             float mx = -INFINITY;
 #pragma unroll
-            for (int g = 0; g < C::MAXNG; g++) {
-                if (g < NG) {
-                    const uint32_t buf = gi % C::NBUF, use = gi / C::NBUF;
-                    gi++;
-                    mbar_wait_parked(&acc_full[buf], use & 1, 200);
-                    tc_fence_after();
-                    const uint32_t tcol = tmem + lane_base + buf * C::N + wg * (C::PW * PC);   // this warpgroup's half of the group
-                    // all TMEM loads of this warpgroup's half are issued back to back (batches of two cluster
-                    // pairs = 4*D registers), ONE wait per batch, and the buffer is handed back to the MMA issuer
-                    // before the arithmetic: the accumulator round trip, not the math, bounds the kernel
-                    constexpr int BATCH = (C::PW >= 2) ? 2 : 1;                  // cluster pairs per batch
-                    static_assert(C::PW % BATCH == 0, "pairs per warpgroup");
-                    auto load_pair = [&](int p, uint32_t (&dst)[PC]) {
-                        if constexpr (D == 24) {
-                            tmem_ld_32x32(tcol + p * PC, *reinterpret_cast<uint32_t(*)[32]>(&dst[0]));
-                            tmem_ld_32x16(tcol + p * PC + 32, *reinterpret_cast<uint32_t(*)[16]>(&dst[32]));
-                        } else if constexpr (D == 16) {
-                            tmem_ld_32x32(tcol + p * PC, *reinterpret_cast<uint32_t(*)[32]>(&dst[0]));
-                        } else {
-                            tmem_ld_32x16(tcol + p * PC, *reinterpret_cast<uint32_t(*)[16]>(&dst[0]));
-                        }
-                    };
+            for (int sg = 0; sg < C::MAXSG; sg++) {
+                if (sg < NSG) {
+                    uint64_t qa[C::CW], qb[C::CW];             // packed partial sums of squares of this warpgroup's 8 clusters
 #pragma unroll
-                    for (int p0 = 0; p0 < C::PW; p0 += BATCH) {
-                        uint32_t v[BATCH][PC];
+                    for (int i = 0; i < C::CW; i++) { qa[i] = 0ull; qb[i] = 0ull; }
 #pragma unroll
-                        for (int b = 0; b < BATCH; b++) load_pair(p0 + b, v[b]);
+                    for (int c = 0; c < C::CP; c++) {
+                        const uint32_t buf = bi % C::NBUF, use = bi / C::NBUF;
+                        bi++;
+                        mbar_wait_parked(&acc_full[buf], use & 1, 200);
+                        tc_fence_after();
+                        const uint32_t tcol = tmem + lane_base + buf * C::N + wg * (C::CW * 8);
+                        uint32_t v[C::CW * 8];                 // 8 clusters x 8 columns
+                        tmem_ld_32x32(tcol, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                        tmem_ld_32x32(tcol + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
                         tmem_ld_wait();
-                        if (p0 + BATCH >= C::PW) {               // every column of this warpgroup's half has been read
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[buf]);   // the block is in registers: hand the buffer back
+#pragma unroll
+                        for (int i = 0; i < C::CW; i++) {
+                            sq_acc2(qa[i], v[i * 8 + 0], v[i * 8 + 1]);
+                            sq_acc2(qb[i], v[i * 8 + 2], v[i * 8 + 3]);
+                            sq_acc2(qa[i], v[i * 8 + 4], v[i * 8 + 5]);
+                            sq_acc2(qb[i], v[i * 8 + 6], v[i * 8 + 7]);
                         }
+                    }
 #pragma unroll
-                        for (int b = 0; b < BATCH; b++) {
-                            const int p = p0 + b;
-#pragma unroll
-                            for (int u = 0; u < 2; u++) {
-                                uint64_t a01 = 0ull, a23 = 0ull;                    // two packed FP32 pairs (FFMA2)
-#pragma unroll
-                                for (int j = 0; j < D; j += 4) {
-                                    sq_acc2(a01, v[b][u * D + j], v[b][u * D + j + 1]);
-                                    sq_acc2(a23, v[b][u * D + j + 2], v[b][u * D + j + 3]);
-                                }
-                                const float qsum = hsum2(a01, a23);
-                                const int cg = wg * (C::PW * 2) + 2 * p + u;           // cluster inside the group
-                                const float l = fmaf(-0.5f, qsum, ck_s[g * C::G + cg]);
-                                lg[g * (C::PW * 2) + 2 * p + u] = l;
-                                mx = fmaxf(mx, l);
-                            }
-                        }
+                    for (int i = 0; i < C::CW; i++) {
+                        const float l = fmaf(-0.5f, hsum2(qa[i], qb[i]), ck_s[sg * C::GB + wg * C::CW + i]);
+                        lg[sg * C::CW + i] = l;
+                        mx = fmaxf(mx, l);
                     }
                 } else {
 #pragma unroll
-                    for (int c = 0; c < C::PW * 2; c++) lg[g * (C::PW * 2) + c] = -INFINITY;
+                    for (int i = 0; i < C::CW; i++) lg[sg * C::CW + i] = -INFINITY;
                 }
             }
             // log-sum-exp over the clusters (estep2, gaussian_kernel.cu:481-503): local part, then the two warpgroups combine
             float sm = 0.f;
 #pragma unroll
             for (int j = 0; j < C::LPT; j++) { lg[j] = __expf(lg[j] - mx); sm += lg[j]; }
-            float2* exb = ex + (it & 1) * (kEWG * 128);
+            float2* exb = ex + (it & 1) * 256;
             exb[wg * 128 + row] = make_float2(mx, sm);
-            named_bar_sync(1, 128 * kEWG);
-            float M = mx;
-#pragma unroll
-            for (int w = 0; w < kEWG; w++) M = fmaxf(M, exb[w * 128 + row].x);
-            float S = 0.f;
-#pragma unroll
-            for (int w = 0; w < kEWG; w++) { const float2 o = exb[w * 128 + row]; S += o.y * __expf(o.x - M); }
+            named_bar_sync(1, 256);
+            const float2 o = exb[(wg ^ 1) * 128 + row];
+            const float M = fmaxf(mx, o.x);
+            const float S = sm * __expf(mx - M) + o.y * __expf(o.x - M);
             const float denom = M + logf(S);                         // :490-494
             const float scale = __expf(mx - M) / S;                  // exp(l - denom) = exp(l - mx) * exp(mx - M) / S
             if (e < n) {
                 if (wg == 0) ll_acc += (double)denom;
-                float* gp = memb + (size_t)(wg * (C::PW * 2)) * pitch + e;      // row of this warpgroup's first cluster
+                float* gp = memb + (size_t)(wg * C::CW) * pitch + e;      // row of this warpgroup's first cluster
 #pragma unroll
-                for (int g = 0; g < C::MAXNG; g++) {
-                    const int kbase = g * C::G + wg * (C::PW * 2);
+                for (int sg = 0; sg < C::MAXSG; sg++) {
+                    const int kbase = sg * C::GB + wg * C::CW;
                     if (kbase < K) {
-                        float* gq = gp + (size_t)(g * C::G) * pitch;
+                        float* gq = gp + (size_t)(sg * C::GB) * pitch;
 #pragma unroll
-                        for (int c = 0; c < C::PW * 2; c++) {
-                            if (kbase + c < K) *gq = lg[g * (C::PW * 2) + c] * scale;   // :498-501
+                        for (int i = 0; i < C::CW; i++) {
+                            if (kbase + i < K) *gq = lg[sg * C::CW + i] * scale;   // :498-501
                             gq += pitch;
                         }
                     }
@@ -740,7 +721,7 @@ bool tc_mstep_supported(int D, int K) {
 }
 bool tc_estep_supported(int D, int K) { return (D == 8 || D == 16 || D == 24) && K >= 1 && K <= 64; }
 
-template <int D> static size_t ecfg_bimg_bytes() { return (size_t)ECfg<D>::MAXNG * ECfg<D>::B_GROUP; }
+template <int D> static size_t ecfg_bimg_bytes() { return (size_t)ECfg<D>::MAXSG * ECfg<D>::B_SG; }
 static size_t bimg_bytes_for(int D) {
     switch (D) { case 8: return ecfg_bimg_bytes<8>(); case 16: return ecfg_bimg_bytes<16>(); case 24: return ecfg_bimg_bytes<24>(); default: return 0; }
 }
@@ -844,37 +825,38 @@ static inline float h2f_bits(uint16_t h) {
 template <int D>
 static int build_bimg(TcState* t, const clusters_t* host, int K, int num_threads) {
     using C = ECfg<D>;
-    const int NG = (K + C::G - 1) / C::G;
+    const int NSG = (K + C::GB - 1) / C::GB;
     for (int k = K; k < 64; k++) t->h_ck[k] = -1e30f;
     int bad = 0;
     (void)num_threads;
 #pragma omp parallel for schedule(static) num_threads(num_threads) if (num_threads > 1 && K >= 8)
-    for (int k = 0; k < NG * C::G; k++) {
-        const int g = k / C::G, cg = k % C::G;
-        // row pointer of MMA column ncol inside group g for K-chunk `chunk` (16 bytes = 8 halves):
-        // K-major SWIZZLE_NONE image [chunk][N rows][16 B]
-        auto rowp = [&](int ncol, int chunk) -> uint16_t* {
-            return reinterpret_cast<uint16_t*>(t->h_bimg + (size_t)g * C::B_GROUP + (size_t)chunk * C::N * 16 + (size_t)ncol * 16);
+    for (int k = 0; k < NSG * C::GB; k++) {
+        const int sg = k / C::GB, i = k % C::GB;
+        // 16-byte K-chunk `chunk` of output column d of this cluster: K-major SWIZZLE_NONE image
+        // [supergroup][block c = d/8][chunk][N = 16 clusters x 8 columns][16 B]
+        auto rowp = [&](int d, int chunk) -> uint16_t* {
+            const int c = d / 8, ncol = i * 8 + (d % 8);
+            return reinterpret_cast<uint16_t*>(t->h_bimg + ((size_t)sg * C::CP + c) * C::B_BLOCK + (size_t)chunk * C::N * 16 + (size_t)ncol * 16);
         };
-        if (k >= K) {                                    // padding cluster of the last group: all-zero rows
+        if (k >= K) {                                    // padding cluster of the last supergroup: all-zero rows
             for (int d = 0; d < D; d++)
-                for (int c = 0; c < C::NCHKB; c++) std::memset(rowp(cg * D + d, c), 0, 16);
+                for (int c = 0; c < C::NCHKB; c++) std::memset(rowp(d, c), 0, 16);
             continue;
         }
         double A[D][D], Gc[D][D];
         const float* Ri = host->Rinv + (size_t)k * D * D;
-        for (int i = 0; i < D; i++)
-            for (int j = 0; j < D; j++) { A[i][j] = 0.5 * ((double)Ri[i * D + j] + (double)Ri[j * D + i]); Gc[i][j] = 0.0; }
+        for (int r = 0; r < D; r++)
+            for (int j = 0; j < D; j++) { A[r][j] = 0.5 * ((double)Ri[r * D + j] + (double)Ri[j * D + r]); Gc[r][j] = 0.0; }
         bool ok = true;
-        for (int j = 0; j < D && ok; j++) {              // Cholesky A = Gc Gc^T
-            double d = A[j][j];
-            for (int p = 0; p < j; p++) d -= Gc[j][p] * Gc[j][p];
+        for (int j = 0; j < D; j++) {                    // right-looking Cholesky A = Gc Gc^T (axpy updates vectorise)
+            const double d = A[j][j];
             if (!(d > 0.0) || !std::isfinite(d)) { ok = false; break; }
-            Gc[j][j] = std::sqrt(d);
-            for (int i = j + 1; i < D; i++) {
-                double v = A[i][j];
-                for (int p = 0; p < j; p++) v -= Gc[i][p] * Gc[j][p];
-                Gc[i][j] = v / Gc[j][j];
+            const double piv = std::sqrt(d), rp = 1.0 / piv;
+            Gc[j][j] = piv;
+            for (int r = j + 1; r < D; r++) Gc[r][j] = A[r][j] * rp;
+            for (int r = j + 1; r < D; r++) {
+                const double l = Gc[r][j];
+                for (int cc = j + 1; cc <= r; cc++) A[r][cc] -= l * Gc[cc][j];
             }
         }
         if (!ok) {
@@ -885,41 +867,51 @@ static int build_bimg(TcState* t, const clusters_t* host, int K, int num_threads
         for (int d = 0; d < D; d++) {
             // row d of W = Gc^T:  W[d][j] = Gc[j][d] (j >= d);  y_d = sum_j W'[d][j] z_j + v_d
             double vd = 0.0;
-            const int ncol = cg * D + d;
-            for (int c = 0; c < C::CP; c++) {
-                uint16_t *ph = rowp(ncol, c), *pl = rowp(ncol, C::CP + c);
-                for (int e = 0; e < 8; e++) {
-                    const int j = c * 8 + e;
-                    const double w = (j >= d) ? Gc[j][d] : 0.0;
-                    const double wp = w * t->h_scale[j];
-                    vd -= w * ((double)host->means[(size_t)k * D + j] - t->h_shift[j]);
-                    const float wf = (float)wp;
-                    if (!(std::fabs(wf) < 6.0e4f)) {
+            alignas(32) float wrow[D];
+            float wmax = 0.f;
+            for (int j = 0; j < D; j++) {
+                const double w = (j >= d) ? Gc[j][d] : 0.0;
+                vd -= w * ((double)host->means[(size_t)k * D + j] - t->h_shift[j]);
+                wrow[j] = (float)(w * t->h_scale[j]);
+                wmax = std::fmax(wmax, std::fabs(wrow[j]));
+            }
+            if (!(wmax < 6.0e4f)) {
 #pragma omp atomic write
-                        bad = 2;
-                    }
-                    const uint16_t wh = f2h_bits(wf);
-                    ph[e] = wh;                                                   // x (zh_c, zl_c), aliased
-                    pl[e] = f2h_bits((float)(wp - (double)h2f_bits(wh)));         // x zh_c
+                bad = 2;
+            }
+            for (int c = 0; c < C::CP; c++) {
+                uint16_t *ph = rowp(d, c), *pl = rowp(d, C::CP + c);      // x (zh_c, zl_c) [aliased], x zh_c
+#if defined(__F16C__) && defined(__AVX__)
+                const __m256 w8 = _mm256_load_ps(wrow + 8 * c);
+                const __m128i h8 = _mm256_cvtps_ph(w8, _MM_FROUND_TO_NEAREST_INT | _MM_FROUND_NO_EXC);
+                const __m256 l8 = _mm256_sub_ps(w8, _mm256_cvtph_ps(h8));  // exact: hi is w rounded to 11 bits
+                _mm_storeu_si128(reinterpret_cast<__m128i*>(ph), h8);
+                _mm_storeu_si128(reinterpret_cast<__m128i*>(pl), _mm256_cvtps_ph(l8, _MM_FROUND_TO_NEAREST_INT | _MM_FROUND_NO_EXC));
+#else
+                for (int e = 0; e < 8; e++) {
+                    const uint16_t wh = f2h_bits(wrow[8 * c + e]);
+                    ph[e] = wh;
+                    pl[e] = f2h_bits(wrow[8 * c + e] - h2f_bits(wh));
                 }
+#endif
             }
             const float vf = (float)vd;
             if (!(std::fabs(vf) < 6.0e4f)) {
 #pragma omp atomic write
                 bad = 2;
             }
-            uint16_t* pv = rowp(ncol, 2 * C::CP);
+            uint16_t* pv = rowp(d, 2 * C::CP);
             const uint16_t vh = f2h_bits(vf);
             std::memset(pv, 0, 16);
             pv[0] = vh;
             pv[1] = f2h_bits((float)(vd - (double)h2f_bits(vh)));
-            if (C::NCHKB > 2 * C::CP + 1) std::memset(rowp(ncol, 2 * C::CP + 1), 0, 16);
+            if (C::NCHKB > 2 * C::CP + 1) std::memset(rowp(d, 2 * C::CP + 1), 0, 16);
         }
         t->h_ck[k] = host->constant[k] + logf(host->pi[k]);  // additive term of estep1 (gaussian_kernel.cu:442)
     }
     if (bad == 1) return fail(GMM_ERR_STATE, "tensor E-step: inverse covariance of a cluster is not positive definite");
     if (bad == 2) return fail(GMM_ERR_STATE, "tensor E-step: whitening factor exceeds the FP16 range");
-    t->e_NG = NG;
+    t->e_NG = NSG;
     return GMM_OK;
 }
 
@@ -935,8 +927,8 @@ int tc_upload_params(TcState* t, const clusters_t* host, int K, cudaStream_t str
         default: return fail(GMM_ERR_ARG, "tensor E-step: unsupported D");
     }
     if (rc) return rc;
-    // only the groups in use travel (the image is contiguous per group)
-    const size_t used = (size_t)t->e_NG * (t->bimg_bytes / (size_t)(64 / (t->D == 24 ? 8 : (t->D == 16 ? 16 : 32))));
+    // only the supergroups in use travel (the image is contiguous per supergroup; 4 supergroups = 64 clusters)
+    const size_t used = (size_t)t->e_NG * (t->bimg_bytes / 4);
     TC_CUDA_TRY(cudaMemcpyAsync(t->d_bimg, t->h_bimg, used, cudaMemcpyHostToDevice, stream));
     TC_CUDA_TRY(cudaMemcpyAsync(t->d_ck, t->h_ck, sizeof(float) * 64, cudaMemcpyHostToDevice, stream));
     return GMM_OK;
