@@ -134,7 +134,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = dict(WORKLOADS[args.workload])
-    metric = "EM iterations/sec at N=10M D=24 K=64" if args.workload == "c3" else \
+    metric = "EM iterations/sec at N=10M D=24 K=64; E-step HBM GB/s vs roofline" if args.workload == "c3" else \
         f"EM iterations/sec at N={wl['N']} D={wl['D']} K={wl['K']}"
     pkg = entry.load_package()
 
@@ -259,8 +259,19 @@ def main():
     e_gbs = e_bytes / (estep_ms * 1e-3) / 1e9 if estep_ms > 0 else 0.0
     m_tfs = m_flops / (mstep_ms * 1e-3) / 1e12 if mstep_ms > 0 else 0.0
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+    # kernels of this repo launched per step: tensor path = mstep_tc_kernel + mstep_tc_finalize_kernel + estep_tc_kernel,
+    # SIMT path = mstep_simt_kernel + estep_simt_kernel (cudaMemsetAsync and the NCCL kernel are not counted)
+    tensor_m = args.path != "simt" and D in (4, 8, 12, 16, 20, 24)
+    launches_per_step = 3 if tensor_m else 2
+    # DRAM traffic per launch of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath) and world == 1:
+        tj = json.load(open(tpath))
+        key = f"{args.workload}:{'tensor' if args.path != 'simt' else 'simt'}:estep"
+        traffic = tj.get(key)
     roofline = dict(kernel="estep", bound="hbm", achieved=e_gbs, peak=peaks["hbm_gbs"], unit="GB/s",
-                    frac=e_gbs / peaks["hbm_gbs"], traffic=None, peak_source=peaks["source"],
+                    frac=e_gbs / peaks["hbm_gbs"], traffic=traffic, peak_source=peaks["source"],
                     ms_per_launch=estep_ms, algorithmic_bytes_per_launch=e_bytes)
     roofline_mstep = dict(kernel="mstep_covariance", bound="tensor", achieved=m_tfs, peak=tf32_peak, unit="TFLOP/s",
                           frac=m_tfs / tf32_peak, peak_source=peaks["source"] + " bf16 sustained / 2 (TF32-equivalent)",
@@ -283,7 +294,7 @@ def main():
                 config=dict(workload=f"{args.workload}: N={N} D={D} K={K} Gaussian blobs (seed {pkg.synth.SEED}), "
                                      f"{count} events on rank 0", path=args.path, l2="inputs (X 0.96 GB + memberships 2.56 GB at c3) exceed the 126 MB L2",
                             parallelism=f"dp{world} (events sharded, one all-reduce of {8 * (K * (1 + D + D * (D + 1) // 2) + 1)} B per step)"),
-                clocks=clocks, e2e=e2e, gpu_launches=2 * args.steps, roofline=roofline, roofline_mstep=roofline_mstep,
+                clocks=clocks, e2e=e2e, gpu_launches=launches_per_step * args.steps, roofline=roofline, roofline_mstep=roofline_mstep,
                 phases_ms_per_step=dict(estep=estep_ms, mstep=mstep_ms, constants_host=prof["constants_host_ms"] / n_estep,
                                         allreduce=prof["allreduce_ms"] / n_estep, upload=prof["upload_ms"] / n_estep),
                 loglik=ll, wall_ms_per_step=dt_wall * 1e3 / args.steps, cpu_baseline=cpu_baseline)
