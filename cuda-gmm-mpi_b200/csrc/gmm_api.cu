@@ -491,6 +491,7 @@ int gmm_set_option(gmm_ctx* c, const char* key, double value) {
         c->path = p;
     } else if (k == "verbose") c->verbose = (int)value;
     else if (k == "host_threads") { c->host_threads = value < 1 ? 1 : (int)value; tc_set_host_threads(c->tc, c->host_threads); }
+    else if (k == "mstep_gamma_split") { tc_set_gamma_split(c->tc, value != 0); }
     else if (k == "write_memberships") { /* accepted; every E-step materialises memberships in this build */ }
     else return fail(GMM_ERR_ARG, "gmm_set_option: unknown key '" + k + "'");
     return GMM_OK;

@@ -140,7 +140,14 @@ __device__ __forceinline__ void build_phi_chunks(const float (&z)[D], uint8_t* h
     }
 }
 
-template <int D>
+// GS: responsibilities enter the MMA as an FP16 hi/lo pair (three products per element).  With GS = false
+// they are rounded once to FP16 (round to nearest, after the 2^10 scaling) and only (phi_hi, g) + (phi_lo, g)
+// are issued: a third less tensor and shared-memory work (measured: -10 % kernel time at N=10M, D=24, K=64).  The rounding perturbs every weight by an unbiased
+// relative error <= 2^-12, consistently in N_k, the first and the second moments, so the result is the exact
+// M-step of weights g(1 + d): the perturbation averages over the events of a cluster (~1e-4 / sqrt(n_eff))
+// and is not amplified by the centring cancellation.  Measured per-call deviation of the means on clusters
+// of ~10 events: 2e-4 without the pair against 5e-6 with it, so the pair is the default.
+template <int D, bool GS>
 __global__ void __launch_bounds__(kMThreads, 1)
 mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g, int n,
                 const float* __restrict__ shift_f, const float* __restrict__ inv_scale_f, double* __restrict__ scratch,
@@ -211,7 +218,7 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 const uint32_t gam = smem_u32(smem + C::OFF_G + os * C::G_STAGE);
                 const uint32_t dcol = tmem + ab * (C::MT * kNCL);
 #pragma unroll
-                for (int seg = 0; seg < 3; seg++) {          // (phi_hi, g_hi), (phi_lo, g_hi), (phi_hi, g_lo)
+                for (int seg = 0; seg < (GS ? 3 : 2); seg++) {   // (phi_hi, g_hi), (phi_lo, g_hi), (phi_hi, g_lo)
                     const uint32_t pa = phi + (seg == 1 ? C::PHI_PART : 0);
                     const uint32_t pb = gam + (seg == 2 ? C::G_PART : 0);
 #pragma unroll
@@ -269,15 +276,21 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 const float4 a = *reinterpret_cast<const float4*>(grow + (((2 * ce) ^ (k & 7)) << 4));
                 const float4 b = *reinterpret_cast<const float4*>(grow + (((2 * ce + 1) ^ (k & 7)) << 4));
                 float g[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                float hi[8], lo[8];
+                if (GS) {
+                    float hi[8], lo[8];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const float v = g[u] * kGammaScale;
-                    hi[u] = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-                    lo[u] = v - hi[u];
+                    for (int u = 0; u < 8; u++) {
+                        const float v = g[u] * kGammaScale;
+                        hi[u] = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+                        lo[u] = v - hi[u];
+                    }
+                    gh[it2] = make_uint4(pack_half2(hi[0], hi[1]), pack_half2(hi[2], hi[3]), pack_half2(hi[4], hi[5]), pack_half2(hi[6], hi[7]));
+                    gl[it2] = make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]), pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7]));
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; u++) g[u] *= kGammaScale;
+                    gh[it2] = make_uint4(pack_half2(g[0], g[1]), pack_half2(g[2], g[3]), pack_half2(g[4], g[5]), pack_half2(g[6], g[7]));
                 }
-                gh[it2] = make_uint4(pack_half2(hi[0], hi[1]), pack_half2(hi[2], hi[3]), pack_half2(hi[4], hi[5]), pack_half2(hi[6], hi[7]));
-                gl[it2] = make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]), pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7]));
             }
             // the raw tiles are in registers now: hand the stage back to the TMA producer before the long part
             __syncwarp();
@@ -299,7 +312,7 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     const int item = bt + it2 * 128;
                     const int kg = item >> 5, l = item & 31;
                     *reinterpret_cast<uint4*>(g_hi + kg * 512 + l * 16) = gh[it2];
-                    *reinterpret_cast<uint4*>(g_hi + C::G_PART + kg * 512 + l * 16) = gl[it2];
+                    if (GS) *reinterpret_cast<uint4*>(g_hi + C::G_PART + kg * 512 + l * 16) = gl[it2];
                 }
             }
             fence_proxy_async_smem();
@@ -435,7 +448,10 @@ template <int D>
 __global__ void __launch_bounds__(kEThreads, 1)
 estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_img, const float* __restrict__ ck,
                 const float* __restrict__ shift_f, const float* __restrict__ inv_scale_f, float* __restrict__ memb,
-                size_t pitch, int n, int K, int NSG, double* __restrict__ ll_out) {
+                size_t pitch, int n, int K, int NSG, double* __restrict__ ll_out, float* __restrict__ den_out) {
+    // K / NSG / b_img / ck / memb describe ONE pass of at most 64 clusters.  With more than 64 clusters the host
+    // launches one pass per 64 (den_out != nullptr): each pass normalises within itself and records its
+    // log-denominator per event; estep_tc_combine_kernel then rescales the passes against each other.
     using C = ECfg<D>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -628,7 +644,10 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
             const float denom = M + logf(S);                         // :490-494
             const float scale = __expf(mx - M) / S;                  // exp(l - denom) = exp(l - mx) * exp(mx - M) / S
             if (e < n) {
-                if (wg == 0) ll_acc += (double)denom;
+                if (wg == 0) {
+                    if (den_out) den_out[e] = denom;
+                    else ll_acc += (double)denom;
+                }
                 float* gp = memb + (size_t)(wg * C::CW) * pitch + e;      // row of this warpgroup's first cluster
 #pragma unroll
                 for (int sg = 0; sg < C::MAXSG; sg++) {
@@ -644,7 +663,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                 }
             }
         }
-        if (wg == 0) {
+        if (wg == 0 && den_out == nullptr) {
             ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 16);
             ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 8);
             ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 4);
@@ -656,6 +675,48 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+// More than 64 clusters: joins the per-pass normalisations.  den[p][e] = ln sum_{k in pass p} exp(logit);
+// the event's denominator is the log-sum-exp over the passes (estep2, gaussian_kernel.cu:481-503) and every
+// responsibility of pass p is multiplied by exp(den_p - denom).
+constexpr int kEMaxPass = GMM_MAX_CLUSTERS / 64;
+__global__ void __launch_bounds__(256)
+estep_tc_combine_kernel(float* __restrict__ memb, size_t pitch, int n, int K, int NP, const float* __restrict__ den,
+                        double* __restrict__ ll_out) {
+    __shared__ double red[8];
+    double ll = 0.0;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        float dp[kEMaxPass];
+        float M = -INFINITY;
+#pragma unroll
+        for (int p = 0; p < kEMaxPass; p++) {
+            dp[p] = p < NP ? den[(size_t)p * pitch + e] : -INFINITY;
+            M = fmaxf(M, dp[p]);
+        }
+        float S = 0.f;
+#pragma unroll
+        for (int p = 0; p < kEMaxPass; p++) S += __expf(dp[p] - M);
+        const float denom = M + logf(S);
+        ll += (double)denom;
+#pragma unroll
+        for (int p = 0; p < kEMaxPass; p++) {
+            if (p < NP) {
+                const float f = __expf(dp[p] - denom);
+                const int kend = min(K, (p + 1) * 64);
+                float* g = memb + (size_t)(p * 64) * pitch + e;
+                for (int k = p * 64; k < kend; k++, g += pitch) *g *= f;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) ll += __shfl_down_sync(0xffffffffu, ll, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ll;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += red[w];
+        atomicAdd(ll_out, t);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -680,10 +741,13 @@ struct TcState {
     uint8_t* d_bimg = nullptr;       // [MAXNG * B_GROUP] resident B operand image
     uint8_t* h_bimg = nullptr;       // pinned
     size_t bimg_bytes = 0;
-    float* d_ck = nullptr;           // [64]
-    float* h_ck = nullptr;           // pinned [64]
+    float* d_ck = nullptr;           // [e_ck_len]
+    float* h_ck = nullptr;           // pinned [e_ck_len]
+    float* d_den = nullptr;          // [passes][memb_pitch] per-pass log-denominators (Kmax > 64 only)
+    int e_ck_len = 0;                // Kmax rounded up to whole passes of 64
     int e_NG = 0;
     int host_threads = 8;
+    bool gamma_split = true;         // M-step: FP16 hi/lo pair for the responsibilities (see mstep_tc_kernel)
     double h_shift[GMM_MAX_DIMENSIONS] = {0}, h_scale[GMM_MAX_DIMENSIONS] = {0};
 };
 
@@ -719,11 +783,12 @@ bool tc_mstep_supported(int D, int K) {
     (void)K;
     return D == 4 || D == 8 || D == 12 || D == 16 || D == 20 || D == 24;
 }
-bool tc_estep_supported(int D, int K) { return (D == 8 || D == 16 || D == 24) && K >= 1 && K <= 64; }
+bool tc_estep_supported(int D, int K) { return (D == 8 || D == 16 || D == 24) && K >= 1 && K <= GMM_MAX_CLUSTERS; }
 
-template <int D> static size_t ecfg_bimg_bytes() { return (size_t)ECfg<D>::MAXSG * ECfg<D>::B_SG; }
-static size_t bimg_bytes_for(int D) {
-    switch (D) { case 8: return ecfg_bimg_bytes<8>(); case 16: return ecfg_bimg_bytes<16>(); case 24: return ecfg_bimg_bytes<24>(); default: return 0; }
+// bytes of the B image of one pass (64 clusters = MAXSG supergroups)
+template <int D> static size_t ecfg_pass_bytes() { return (size_t)ECfg<D>::MAXSG * ECfg<D>::B_SG; }
+static size_t pass_bytes_for(int D) {
+    switch (D) { case 8: return ecfg_pass_bytes<8>(); case 16: return ecfg_pass_bytes<16>(); case 24: return ecfg_pass_bytes<24>(); default: return 0; }
 }
 
 int tc_create(TcState** out, const float* d_x_aos, const float* d_x_soa, int n, int D, int Kmax, float* d_memb, size_t memb_pitch, int num_sms,
@@ -742,11 +807,14 @@ int tc_create(TcState** out, const float* d_x_aos, const float* d_x_soa, int n, 
     if (int rc = make_map_2d(&t->tm_g, d_memb, (uint64_t)n, (uint64_t)Kmax, (uint64_t)memb_pitch * 4, kTE, kNCL, /*swizzle128=*/true)) return rc;
     t->maps_ok = true;
     if (D == 8 || D == 16 || D == 24) {
-        t->bimg_bytes = bimg_bytes_for(D);
+        const int passes = (Kmax + 63) / 64;
+        t->e_ck_len = passes * 64;
+        t->bimg_bytes = (size_t)passes * pass_bytes_for(D);
         TC_CUDA_TRY(cudaMalloc(&t->d_bimg, t->bimg_bytes));
         TC_CUDA_TRY(cudaMallocHost(&t->h_bimg, t->bimg_bytes));
-        TC_CUDA_TRY(cudaMalloc(&t->d_ck, sizeof(float) * 64));
-        TC_CUDA_TRY(cudaMallocHost(&t->h_ck, sizeof(float) * 64));
+        TC_CUDA_TRY(cudaMalloc(&t->d_ck, sizeof(float) * t->e_ck_len));
+        TC_CUDA_TRY(cudaMallocHost(&t->h_ck, sizeof(float) * t->e_ck_len));
+        if (passes > 1) TC_CUDA_TRY(cudaMalloc(&t->d_den, sizeof(float) * (size_t)passes * memb_pitch));
         t->emap_ok = true;
     }
     const int mt = (num_features(D) + 127) / 128;
@@ -757,11 +825,12 @@ int tc_create(TcState** out, const float* d_x_aos, const float* d_x_soa, int n, 
 }
 
 void tc_set_host_threads(TcState* t, int n) { if (t) t->host_threads = n < 1 ? 1 : n; }
+void tc_set_gamma_split(TcState* t, bool on) { if (t) t->gamma_split = on; }
 
 void tc_destroy(TcState* t) {
     if (!t) return;
     cudaFree(t->d_shift_f); cudaFree(t->d_inv_scale_f); cudaFree(t->d_scale); cudaFree(t->d_scratch);
-    cudaFree(t->d_bimg); cudaFree(t->d_ck);
+    cudaFree(t->d_bimg); cudaFree(t->d_ck); cudaFree(t->d_den);
     if (t->h_bimg) cudaFreeHost(t->h_bimg);
     if (t->h_ck) cudaFreeHost(t->h_ck);
     delete t;
@@ -826,7 +895,7 @@ template <int D>
 static int build_bimg(TcState* t, const clusters_t* host, int K, int num_threads) {
     using C = ECfg<D>;
     const int NSG = (K + C::GB - 1) / C::GB;
-    for (int k = K; k < 64; k++) t->h_ck[k] = -1e30f;
+    for (int k = K; k < t->e_ck_len; k++) t->h_ck[k] = -1e30f;
     int bad = 0;
     (void)num_threads;
 #pragma omp parallel for schedule(static) num_threads(num_threads) if (num_threads > 1 && K >= 8)
@@ -928,9 +997,9 @@ int tc_upload_params(TcState* t, const clusters_t* host, int K, cudaStream_t str
     }
     if (rc) return rc;
     // only the supergroups in use travel (the image is contiguous per supergroup; 4 supergroups = 64 clusters)
-    const size_t used = (size_t)t->e_NG * (t->bimg_bytes / 4);
+    const size_t used = (size_t)t->e_NG * (pass_bytes_for(t->D) / 4);
     TC_CUDA_TRY(cudaMemcpyAsync(t->d_bimg, t->h_bimg, used, cudaMemcpyHostToDevice, stream));
-    TC_CUDA_TRY(cudaMemcpyAsync(t->d_ck, t->h_ck, sizeof(float) * 64, cudaMemcpyHostToDevice, stream));
+    TC_CUDA_TRY(cudaMemcpyAsync(t->d_ck, t->h_ck, sizeof(float) * t->e_ck_len, cudaMemcpyHostToDevice, stream));
     return GMM_OK;
 }
 
@@ -947,9 +1016,20 @@ static int launch_estep_d(TcState* t, int K, double* d_ll, cudaStream_t stream) 
     int grid = t->num_sms;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) grid = 1;
-    estep_tc_kernel<D><<<grid, kEThreads, C::SMEM_BYTES, stream>>>(t->d_x, t->d_bimg, t->d_ck, t->d_shift_f, t->d_inv_scale_f,
-                                                                   t->d_memb, t->memb_pitch, t->n, K, t->e_NG, d_ll);
-    TC_CUDA_TRY(cudaGetLastError());
+    const int NP = (K + 63) / 64;
+    if (NP > 1 && !t->d_den) return fail(GMM_ERR_STATE, "tensor E-step: context was created for at most 64 clusters");
+    for (int p = 0; p < NP; p++) {
+        const int Kp = K - 64 * p < 64 ? K - 64 * p : 64;
+        estep_tc_kernel<D><<<grid, kEThreads, C::SMEM_BYTES, stream>>>(
+            t->d_x, t->d_bimg + (size_t)p * C::MAXSG * C::B_SG, t->d_ck + 64 * p, t->d_shift_f, t->d_inv_scale_f,
+            t->d_memb + (size_t)(64 * p) * t->memb_pitch, t->memb_pitch, t->n, Kp, (Kp + C::GB - 1) / C::GB, d_ll,
+            NP > 1 ? t->d_den + (size_t)p * t->memb_pitch : nullptr);
+        TC_CUDA_TRY(cudaGetLastError());
+    }
+    if (NP > 1) {
+        estep_tc_combine_kernel<<<t->num_sms * 8, 256, 0, stream>>>(t->d_memb, t->memb_pitch, t->n, K, NP, t->d_den, d_ll);
+        TC_CUDA_TRY(cudaGetLastError());
+    }
     return GMM_OK;
 }
 
@@ -970,7 +1050,8 @@ static int launch_mstep_d(TcState* t, int K, double* d_stats, cudaStream_t strea
     static_assert(C::TMEM_COLS <= 512, "TMEM budget");
     static bool attr = false;
     if (!attr) {
-        TC_CUDA_TRY(cudaFuncSetAttribute(mstep_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        TC_CUDA_TRY(cudaFuncSetAttribute(mstep_tc_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        TC_CUDA_TRY(cudaFuncSetAttribute(mstep_tc_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr = true;
     }
     int gx = t->num_sms;
@@ -981,8 +1062,12 @@ static int launch_mstep_d(TcState* t, int K, double* d_stats, cudaStream_t strea
     if ((size_t)gx * gy * C::MT * 128 * kNCL > t->scratch_floats) return fail(GMM_ERR_STATE, "tensor M-step scratch too small");
     dim3 grid(gx, gy);
     TC_CUDA_TRY(cudaMemsetAsync(t->d_scratch, 0, sizeof(double) * (size_t)gx * gy * C::MT * 128 * kNCL, stream));
-    mstep_tc_kernel<D><<<grid, kMThreads, C::SMEM_BYTES, stream>>>(t->tm_x, t->tm_g, t->n, t->d_shift_f, t->d_inv_scale_f,
-                                                                   t->d_scratch, per);
+    if (t->gamma_split)
+        mstep_tc_kernel<D, true><<<grid, kMThreads, C::SMEM_BYTES, stream>>>(t->tm_x, t->tm_g, t->n, t->d_shift_f, t->d_inv_scale_f,
+                                                                             t->d_scratch, per);
+    else
+        mstep_tc_kernel<D, false><<<grid, kMThreads, C::SMEM_BYTES, stream>>>(t->tm_x, t->tm_g, t->n, t->d_shift_f, t->d_inv_scale_f,
+                                                                              t->d_scratch, per);
     TC_CUDA_TRY(cudaGetLastError());
     const int F = C::F;
     mstep_tc_finalize_kernel<<<(K * F + 255) / 256, 256, 0, stream>>>(t->d_scratch, gx, C::MT, K, D, F, t->d_scale, d_stats);

@@ -17,6 +17,8 @@ int  tc_create(TcState** out, const float* d_x_aos, const float* d_x_soa, int n,
                int num_sms, cudaStream_t stream);
 void tc_destroy(TcState*);
 void tc_set_host_threads(TcState*, int n);
+// M-step responsibilities as an FP16 hi/lo pair (true, default) or one round-to-nearest FP16 value (false).
+void tc_set_gamma_split(TcState*, bool on);
 // Centre/scale used inside the tensor kernels: z = (x - shift) * inv_scale, both rounded to
 // float; `shift` is updated in place to the float-rounded values actually used.
 int  tc_set_shift_scale(TcState*, double* shift, const double* scale, cudaStream_t stream);

@@ -98,7 +98,11 @@ int  gmm_comm_rank(const gmm_ctx*, int* rank, int* nranks);
 /* ---- options: the reference's compile-time #defines made runtime
  * (gaussian.h:23-38).  Known keys: "path" (GMM_PATH_*), "verbose",
  * "write_memberships" (1 = every E-step materialises memberships, as the
- * reference does; 0 = only gmm_estep()/gmm_get_clusters() do).             */
+ * reference does; 0 = only gmm_estep()/gmm_get_clusters() do),
+ * "host_threads" (threads of the host-side finalisation),
+ * "mstep_gamma_split" (tensor M-step: 1 (default) = responsibilities enter
+ * the MMA as an FP16 hi/lo pair, 0 = one round-to-nearest FP16 value:
+ * 10 % faster kernel, 1e-4/sqrt(n_k) statistical error per cluster).      */
 int  gmm_set_option(gmm_ctx*, const char* key, double value);
 
 /* ---- operators (one per reference kernel group) ------------------------- */

@@ -26,7 +26,7 @@ def assert_memb_close(got, ref, rtol=1e-4, atol=1e-6):
     np.testing.assert_allclose(got, ref, rtol=rtol, atol=atol)
 
 
-def run_level_check(got, ref, K, path):
+def run_level_check(got, ref, K, path, tensor_memb_atol=4e-3):
     """Parity after many EM iterations.
     SIMT path (FP32 E-step, exact FP64 M-step statistics): the calibrated run-level bar of conftest.py
     (measured deviation from the exact oracle: 6e-6 on responsibilities after 100 iterations at config 1).
@@ -41,7 +41,7 @@ def run_level_check(got, ref, K, path):
         assert_memb_close(got.memberships, ref.memberships, **RUN_MEMB)
     else:
         assert_params_close(got, ref, K, rtol=2e-3, rtol_N=3e-3)
-        assert_memb_close(got.memberships, ref.memberships, rtol=1e-2, atol=4e-3)
+        assert_memb_close(got.memberships, ref.memberships, rtol=1e-2, atol=tensor_memb_atol)
 
 
 @pytest.fixture(scope="module")
@@ -113,10 +113,12 @@ def test_mstep_constants_parity(loaded, oracle64, path, N, D, K):
     assert_params_close(got, ref, K)
 
 
-@pytest.mark.parametrize("N,D,K", [(300_000, 24, 64), (150_001, 16, 32), (100_003, 24, 17), (65_000, 8, 64), (257, 16, 5)])
+@pytest.mark.parametrize("N,D,K", [(300_000, 24, 64), (150_001, 16, 32), (100_003, 24, 17), (65_000, 8, 64), (257, 16, 5),
+                                   (60_001, 24, 128), (30_001, 16, 100), (20_000, 8, 200)])
 def test_estep_tensor_path_large(loaded, oracle64, N, D, K):
-    """The tcgen05 E-step (CTA pairs, resident whitening factors) over many tiles per pair,
-    odd event counts (partial last tile) and cluster counts that do not fill an MMA group."""
+    """The tcgen05 E-step (resident whitening factors) over many tiles per CTA, odd event counts
+    (partial last tile), cluster counts that do not fill an MMA group, and more than 64 clusters
+    (one pass per 64 clusters + the combine kernel)."""
     pkg = loaded
     ev = pkg.synth.make_blobs(N, D, min(K, 16), seed=400 + D)
     ref = fitted_params(pkg, oracle64, ev, K, iters=1)
@@ -209,6 +211,28 @@ def test_em_config2_slice(loaded, oracle64, path):
     assert it == 10
     assert abs(ll - ll_ref) <= 1e-5 * abs(ll_ref)
     run_level_check(got, ref, K, path)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_em_config5_slice(loaded, oracle64, path):
+    """BASELINE config 5 shape (D=24, K=128: two 64-cluster passes on the tensor path) on a
+    40k-event slice, 5 iterations.  128 clusters on 32 blobs: four clusters compete for each blob, so a
+    handful of boundary events (3 of 5.1M on a B200) move by up to 1.2e-2 on the tensor path
+    (scripts/exp_gsplit.py); parameters stay inside the run-level bars."""
+    pkg = loaded
+    N, D, K = 40_000, 24, 128
+    ev = pkg.synth.make_blobs(N, D, 32, seed=55)
+    ref = pkg.Clusters(K, D, N)
+    oracle64.seed(ev, K, ref)
+    ll_ref, _ = oracle64.em(oracle64.transpose(ev), ref, K, 5, 5)
+    with pkg.Engine(ev, K) as eng:
+        eng.set_option("path", path_id(pkg, path))
+        eng.seed(K)
+        ll, it = eng.em(K, 5, 5)
+        got = eng.get_clusters(K, with_memberships=True)
+    assert it == 5
+    assert abs(ll - ll_ref) <= 1e-5 * abs(ll_ref)
+    run_level_check(got, ref, K, path, tensor_memb_atol=3e-2)
 
 
 @pytest.mark.parametrize("path", PATHS)
