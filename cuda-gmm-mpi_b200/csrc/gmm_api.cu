@@ -396,7 +396,8 @@ int gmm_create(gmm_ctx** out, int device, int n_local, int D, int Kmax, const fl
     CREATE_TRY(cudaMalloc(&c->d_x_aos, sizeof(float) * nmax * D));
     c->memb_pitch = (nmax + 31) / 32 * 32;         // also the row pitch of the SoA event copy
     CREATE_TRY(cudaMalloc(&c->d_x_soa, sizeof(float) * c->memb_pitch * D));
-    CREATE_TRY(cudaMalloc(&c->d_memb, sizeof(float) * c->memb_pitch * Kmax));
+    // rows in multiples of 8: the tensor E-step stores whole 8-cluster groups (zeros for the padding clusters)
+    CREATE_TRY(cudaMalloc(&c->d_memb, sizeof(float) * c->memb_pitch * (size_t)((Kmax + 7) / 8 * 8)));
     CREATE_TRY(cudaMalloc(&c->d_epack, sizeof(float) * (size_t)Kmax * epack_stride(D)));
     CREATE_TRY(cudaMallocHost(&c->h_epack, sizeof(float) * (size_t)Kmax * epack_stride(D)));
     CREATE_TRY(cudaMalloc(&c->d_stats, sizeof(double) * ((size_t)Kmax * c->F + 1)));

@@ -476,7 +476,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
         mbar_init(b_full, 1);
         fence_mbar_init();
     }
-    if (threadIdx.x < 64) ck_s[threadIdx.x] = ck[threadIdx.x];
+    if (threadIdx.x < 64) ck_s[threadIdx.x] = ck[threadIdx.x] * 1.4426950408889634f;   // base-2 logits in the epilogue
     if (threadIdx.x < D) { sh_s[threadIdx.x] = shift_f[threadIdx.x]; isc_s[threadIdx.x] = inv_scale_f[threadIdx.x]; }
     __syncthreads();
     if (threadIdx.x == 0) {                    // resident B operand: one TMA bulk copy per block
@@ -497,17 +497,18 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
         // ===================== MMA issuer =====================
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(128, C::N, false, false);
-            uint32_t bi = 0;                                   // running block index: buffer = bi % NBUF
+            uint32_t pe = (1u << C::NBUF) - 1u;                // wait parity of acc_empty[b], one bit per buffer
             for (int it = 0; it < my_tiles; it++) {
                 const int as = it & 1, aph = (it >> 1) & 1;
                 mbar_wait_parked(&a_full[as], aph, 200);
                 tc_fence_after();
                 const uint32_t abase = smem_u32(smem + C::OFF_A + as * C::A_STAGE);
+                uint32_t buf = 0;                              // the buffer sequence restarts with every tile (epilogue: same rule)
                 for (int sg = 0; sg < NSG; sg++) {
 #pragma unroll
-                    for (int c = 0; c < C::CP; c++, bi++) {
-                        const uint32_t buf = bi % C::NBUF, use = bi / C::NBUF;
-                        mbar_wait_parked(&acc_empty[buf], (use & 1) ^ 1, 100);
+                    for (int c = 0; c < C::CP; c++) {
+                        mbar_wait_parked(&acc_empty[buf], (pe >> buf) & 1u, 100);
+                        pe ^= 1u << buf;
                         tc_fence_after();
                         const uint32_t bbase = smem_u32(smem + C::OFF_B + (sg * C::CP + c) * C::B_BLOCK);
                         bool acc = false;
@@ -528,6 +529,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                             }
                         }
                         mma_commit(&acc_full[buf]);
+                        buf = (buf + 1) % C::NBUF;
                     }
                 }
                 mma_commit(&a_empty[as]);
@@ -587,10 +589,13 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         double ll_acc = 0.0;
-        uint32_t bi = 0;                                       // running block index, as in the MMA issuer
+        uint32_t pf[C::NBUF];                                  // wait parity of acc_full[b]; b is static after unrolling
+#pragma unroll
+        for (int b = 0; b < C::NBUF; b++) pf[b] = 0u;
+        constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
         for (int it = 0; it < my_tiles; it++) {
             const long long e = (long long)((int)blockIdx.x + it * (int)gridDim.x) * 128 + row;
-            float lg[C::LPT];
+            float lg[C::LPT];                                  // logits in base 2 (ck_s is pre-multiplied by log2 e)
             float mx = -INFINITY;
 #pragma unroll
             for (int sg = 0; sg < C::MAXSG; sg++) {
@@ -600,9 +605,9 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                     for (int i = 0; i < C::CW; i++) { qa[i] = 0ull; qb[i] = 0ull; }
 #pragma unroll
                     for (int c = 0; c < C::CP; c++) {
-                        const uint32_t buf = bi % C::NBUF, use = bi / C::NBUF;
-                        bi++;
-                        mbar_wait_parked(&acc_full[buf], use & 1, 200);
+                        const int buf = (sg * C::CP + c) % C::NBUF;   // compile-time: the sequence restarts with every tile
+                        mbar_wait_parked(&acc_full[buf], pf[buf], 200);
+                        pf[buf] ^= 1u;
                         tc_fence_after();
                         const uint32_t tcol = tmem + lane_base + buf * C::N + wg * (C::CW * 8);
                         uint32_t v[C::CW * 8];                 // 8 clusters x 8 columns
@@ -622,7 +627,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                     }
 #pragma unroll
                     for (int i = 0; i < C::CW; i++) {
-                        const float l = fmaf(-0.5f, hsum2(qa[i], qb[i]), ck_s[sg * C::GB + wg * C::CW + i]);
+                        const float l = fmaf(-0.5f * kLog2e, hsum2(qa[i], qb[i]), ck_s[sg * C::GB + wg * C::CW + i]);
                         lg[sg * C::CW + i] = l;
                         mx = fmaxf(mx, l);
                     }
@@ -634,29 +639,31 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
             // log-sum-exp over the clusters (estep2, gaussian_kernel.cu:481-503): local part, then the two warpgroups combine
             float sm = 0.f;
 #pragma unroll
-            for (int j = 0; j < C::LPT; j++) { lg[j] = __expf(lg[j] - mx); sm += lg[j]; }
+            for (int j = 0; j < C::LPT; j++) { lg[j] = ex2_approx(lg[j] - mx); sm += lg[j]; }
             float2* exb = ex + (it & 1) * 256;
             exb[wg * 128 + row] = make_float2(mx, sm);
             named_bar_sync(1, 256);
             const float2 o = exb[(wg ^ 1) * 128 + row];
             const float M = fmaxf(mx, o.x);
-            const float S = sm * __expf(mx - M) + o.y * __expf(o.x - M);
-            const float denom = M + logf(S);                         // :490-494
-            const float scale = __expf(mx - M) / S;                  // exp(l - denom) = exp(l - mx) * exp(mx - M) / S
+            const float own = ex2_approx(mx - M);
+            const float S = sm * own + o.y * ex2_approx(o.x - M);
+            const float denom = fmaf(M, kLn2, logf(S));              // :490-494, back in natural units
+            const float scale = own / S;                             // exp(l - denom) = 2^(l2 - mx) * 2^(mx - M) / S
             if (e < n) {
                 if (wg == 0) {
                     if (den_out) den_out[e] = denom;
                     else ll_acc += (double)denom;
                 }
+                // Rows [K, 8*ceil(K/8)) are written too (zeros of the padding clusters): the buffer is allocated in
+                // multiples of 8 rows, which keeps the 8 stores of a group unpredicated.
                 float* gp = memb + (size_t)(wg * C::CW) * pitch + e;      // row of this warpgroup's first cluster
 #pragma unroll
                 for (int sg = 0; sg < C::MAXSG; sg++) {
-                    const int kbase = sg * C::GB + wg * C::CW;
-                    if (kbase < K) {
+                    if (sg * C::GB + wg * C::CW < K) {
                         float* gq = gp + (size_t)(sg * C::GB) * pitch;
 #pragma unroll
                         for (int i = 0; i < C::CW; i++) {
-                            if (kbase + i < K) *gq = lg[sg * C::CW + i] * scale;   // :498-501
+                            *gq = lg[sg * C::CW + i] * scale;             // :498-501
                             gq += pitch;
                         }
                     }

@@ -177,6 +177,13 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     return r;
 }
 
+// 2^x, MUFU.EX2 (denormal results flush to zero; callers pass x <= 0)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // ---- thread-block clusters / CTA pairs (cta_group::2) --------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
