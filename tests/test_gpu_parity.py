@@ -278,6 +278,26 @@ def test_fit_order_reduction(loaded, oracle64, path):
 
 
 @pytest.mark.parametrize("path", PATHS)
+def test_fit_config5_shape(loaded, oracle64, path):
+    """Order-reduction loop at the config-5 shape (D=24, more than 64 clusters, reduced to a target):
+    the tensor path runs the two-pass E-step while K > 64 and the single-pass one afterwards."""
+    pkg = loaded
+    N, D, K0, target = 12_000, 24, 72, 60
+    ev = pkg.synth.make_blobs(N, D, 24, seed=77)
+    c, s = pkg.Clusters(K0, D, N), pkg.Clusters(K0, D, N)
+    ideal_ref, mr_ref = oracle64.fit(ev, K0, target, 3, 3, c, s)
+    with pkg.Engine(ev, K0) as eng:
+        eng.set_option("path", path_id(pkg, path))
+        ideal, mr, saved = eng.fit(K0, target, 3, 3)
+    assert ideal == ideal_ref
+    assert abs(mr - mr_ref) <= 1e-4 * abs(mr_ref)
+    if path == "simt":
+        assert_params_close(saved, s, ideal, rtol=5e-4)
+    else:
+        assert_params_close(saved, s, ideal, rtol=2e-3, rtol_N=3e-3)
+
+
+@pytest.mark.parametrize("path", PATHS)
 def test_full_size_properties_config2(loaded, path):
     """Config 2 at full size (N=1M, D=16, K=32): size-independent properties —
     responsibilities sum to 1, sum_k N_k = N, covariances symmetric positive
