@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gmm.h"
@@ -113,6 +114,7 @@ struct gmm_ctx {
     int path = GMM_PATH_AUTO;
     int verbose = 0;
     int host_threads = 1;
+    bool host_threads_fixed = false; // set by GMM_HOST_THREADS / gmm_set_option: not re-derived from the rank count
     // profile
     PhaseTimer t_estep, t_mstep, t_reduce, t_fused;
     double host_const_ms = 0, memcpy_ms = 0;
@@ -158,6 +160,16 @@ static void copy_params(clusters_t* dst, const clusters_t* src, int K, int D) {
     std::memcpy(dst->Rinv, src->Rinv, sizeof(float) * (size_t)K * D * D);
 }
 
+// Threads of the replicated host finalisation (K independent D x D inversions + factorizations, ~5 us each):
+// a share of the box's cores, at most 16 (beyond that the fork/join costs more than it saves).
+static int default_host_threads(int ranks_on_box) {
+    const int hw = (int)std::thread::hardware_concurrency();
+    int t = hw > 0 ? hw / (ranks_on_box > 0 ? ranks_on_box : 1) : 8;
+    if (t > 16) t = 16;
+    if (t < 1) t = 1;
+    return t;
+}
+
 static bool use_tensor_estep(const gmm_ctx* c, int K) { return c->path != GMM_PATH_SIMT && c->n > 0 && tc_estep_supported(c->D, K); }
 static bool use_tensor_mstep(const gmm_ctx* c, int K) { return c->path != GMM_PATH_SIMT && c->n > 0 && tc_mstep_supported(c->D, K); }
 // GMM_PATH_TENSOR never degrades silently: the M-step (the covariance contraction) must be covered.
@@ -172,18 +184,36 @@ static int ensure_moments(gmm_ctx* c);
 // Upload the current host parameters in the form the E-step kernels consume
 // (gaussian.cu:446-452 / 935-941 upload the seven raw arrays; here the E-step
 // operand is pre-packed on the host once per iteration).
-static int upload_params(gmm_ctx* c, int K) {
+// with_constants: the inverse / constant / pi of every cluster still have to be derived from R (M-step
+// finalisation).  On the tensor path that work shares ONE parallel loop over the clusters with the E-step
+// operand (Cholesky + FP16 split): one thread-team wake-up per EM iteration instead of two.
+static int upload_params(gmm_ctx* c, int K, bool with_constants = false) {
     if (int rc = check_path(c, K)) return rc;
     auto t0 = std::chrono::steady_clock::now();
     c->estep_tensor_ready = false;
     if (use_tensor_estep(c, K)) {
         if (int rc = ensure_moments(c)) return rc;
-        const int rc = tc_upload_params(c->tc, &c->host, K, c->stream);
+        int rc = tc_params_begin(c->tc, K, c->stream);
+        if (rc == GMM_OK) {
+            if (with_constants) mixing_weights(K, &c->host);
+            const int kp = tc_params_padded(c->tc, K), nt = c->host_threads, D = c->D;
+            int bad = 0;
+            (void)nt;
+#pragma omp parallel for schedule(static) num_threads(nt) reduction(max : bad) if (nt > 1 && K >= 8)
+            for (int k = 0; k < kp; k++) {
+                if (with_constants && k < K) constants_cluster(k, D, &c->host);
+                const int b = tc_params_cluster(c->tc, &c->host, k, K);
+                bad = b > bad ? b : bad;
+            }
+            with_constants = false;
+            rc = tc_params_commit(c->tc, K, bad, c->stream);
+        }
         if (rc == GMM_OK) c->estep_tensor_ready = true;
         else if (rc != GMM_ERR_STATE || c->path == GMM_PATH_TENSOR) return rc;
         // GMM_ERR_STATE under GMM_PATH_AUTO: a cluster whose inverse covariance is not positive definite
         // (or does not fit FP16) — this parameter set is evaluated by the FP32 SIMT kernel instead.
     }
+    if (with_constants) constants_from_R(K, c->D, &c->host, c->host_threads);
     if (!c->estep_tensor_ready) {
         build_epack(K, c->D, &c->host, c->h_epack);
         CUDA_TRY(cudaMemcpyAsync(c->d_epack, c->h_epack, sizeof(float) * (size_t)K * epack_stride(c->D),
@@ -302,9 +332,9 @@ static int reduce_stats_to_host(gmm_ctx* c, int K) {
 
 static int finalize_and_upload(gmm_ctx* c, int K) {
     auto t0 = std::chrono::steady_clock::now();
-    finalize_from_stats(c->h_stats, c->shift, K, c->D, &c->host, c->host_threads);
+    finalize_from_stats(c->h_stats, c->shift, K, c->D, &c->host, c->host_threads, /*with_constants=*/false);
     c->host_const_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    return upload_params(c, K);
+    return upload_params(c, K, /*with_constants=*/true);   // inverse, constants, pi + E-step operand (timed as "upload")
 }
 
 // Global column moments (sum x, sum x^2 over ALL events of all ranks), computed once per
@@ -377,7 +407,8 @@ int gmm_create(gmm_ctx** out, int device, int n_local, int D, int Kmax, const fl
     c->device = device; c->n = n_local; c->D = D; c->Kmax = Kmax; c->F = num_features(D);
     c->n_global = n_global; c->offset = offset; c->num_sms = prop.multiProcessorCount;
     const char* ht = getenv("GMM_HOST_THREADS");
-    c->host_threads = ht ? atoi(ht) : 8;
+    c->host_threads_fixed = ht != nullptr;
+    c->host_threads = ht ? atoi(ht) : default_host_threads(1);
     if (c->host_threads < 1) c->host_threads = 1;
     c->hN.assign(Kmax, 0); c->hpi.assign(Kmax, 0); c->hconst.assign(Kmax, 0); c->havgvar.assign(Kmax, 0);
     c->hmeans.assign((size_t)Kmax * D, 0); c->hR.assign((size_t)Kmax * D * D, 0); c->hRinv.assign((size_t)Kmax * D * D, 0);
@@ -466,6 +497,10 @@ int gmm_nccl_unique_id(char id_out[128]) {
 int gmm_comm_init(gmm_ctx* c, int nranks, int rank, const char id_in[128]) {
     if (!c || nranks < 1 || rank < 0 || rank >= nranks) return fail(GMM_ERR_ARG, "gmm_comm_init: bad argument");
     c->rank = rank; c->nranks = nranks;
+    if (!c->host_threads_fixed) {                   // the ranks of one box share its cores
+        c->host_threads = default_host_threads(nranks);
+        tc_set_host_threads(c->tc, c->host_threads);
+    }
     if (nranks == 1) return GMM_OK;
     if (!id_in) return fail(GMM_ERR_ARG, "gmm_comm_init: null id");
     if (!nccl().ok) return fail(GMM_ERR_NCCL, "libnccl.so.2 not found");
@@ -491,7 +526,11 @@ int gmm_set_option(gmm_ctx* c, const char* key, double value) {
         if (p < GMM_PATH_AUTO || p > GMM_PATH_TENSOR) return fail(GMM_ERR_ARG, "gmm_set_option: bad path");
         c->path = p;
     } else if (k == "verbose") c->verbose = (int)value;
-    else if (k == "host_threads") { c->host_threads = value < 1 ? 1 : (int)value; tc_set_host_threads(c->tc, c->host_threads); }
+    else if (k == "host_threads") {
+        c->host_threads = value < 1 ? 1 : (int)value;
+        c->host_threads_fixed = true;
+        tc_set_host_threads(c->tc, c->host_threads);
+    }
     else if (k == "mstep_gamma_split") { tc_set_gamma_split(c->tc, value != 0); }
     else if (k == "write_memberships") { /* accepted; every E-step materialises memberships in this build */ }
     else return fail(GMM_ERR_ARG, "gmm_set_option: unknown key '" + k + "'");

@@ -66,23 +66,29 @@ static const double kPi = 3.1415926535897931;   // gaussian.h:11
 // constants_kernel (gaussian_kernel.cu:250-259): compute_constants (196-243)
 // per cluster + compute_pi (172-193).  Inversion in double, results stored as
 // float like the reference's clusters_t.
-void constants_from_R(int K, int D, clusters_t* c, int num_threads) {
-    (void)num_threads;
-#pragma omp parallel for schedule(static) num_threads(num_threads) if (K >= 8 && num_threads > 1)
-    for (int k = 0; k < K; k++) {
-        double m[GMM_MAX_DIMENSIONS * GMM_MAX_DIMENSIONS], w[GMM_MAX_DIMENSIONS * GMM_MAX_DIMENSIONS];
-        const float* R = c->R + (size_t)k * D * D;
-        for (int i = 0; i < D * D; i++) m[i] = R[i];
-        double ld;
-        lu_inverse_nopivot<double>(m, D, &ld, w);
-        float* Ri = c->Rinv + (size_t)k * D * D;
-        for (int i = 0; i < D * D; i++) Ri[i] = (float)m[i];
-        c->constant[k] = (float)(-D * 0.5 * std::log(2.0 * kPi) - 0.5 * ld);   // :241
-    }
+void constants_cluster(int k, int D, clusters_t* c) {
+    double m[GMM_MAX_DIMENSIONS * GMM_MAX_DIMENSIONS], w[GMM_MAX_DIMENSIONS * GMM_MAX_DIMENSIONS];
+    const float* R = c->R + (size_t)k * D * D;
+    for (int i = 0; i < D * D; i++) m[i] = R[i];
+    double ld;
+    lu_inverse_nopivot<double>(m, D, &ld, w);
+    float* Ri = c->Rinv + (size_t)k * D * D;
+    for (int i = 0; i < D * D; i++) Ri[i] = (float)m[i];
+    c->constant[k] = (float)(-D * 0.5 * std::log(2.0 * kPi) - 0.5 * ld);   // :241
+}
+
+void mixing_weights(int K, clusters_t* c) {
     double sum = 0;                                                            // :176-181
     for (int k = 0; k < K; k++) sum += c->N[k];
     for (int k = 0; k < K; k++)                                                // :184-190
         c->pi[k] = (c->N[k] < 0.5f) ? 1e-10f : (float)(c->N[k] / sum);
+}
+
+void constants_from_R(int K, int D, clusters_t* c, int num_threads) {
+    (void)num_threads;
+#pragma omp parallel for schedule(static) num_threads(num_threads) if (K >= 8 && num_threads > 1)
+    for (int k = 0; k < K; k++) constants_cluster(k, D, c);
+    mixing_weights(K, c);
 }
 
 // Host side of the M-step (gaussian.cu:611-622 means, :663-679 covariance)

@@ -28,6 +28,10 @@ void finalize_from_stats(const double* stats, const double* shift, int K, int D,
 
 // constants_kernel semantics on host arrays: Rinv, constant (ln det), pi.
 void constants_from_R(int K, int D, clusters_t* c, int num_threads);
+// The two parts of constants_from_R, for callers that run their own loop over the clusters:
+// inverse + constant of one cluster, and the mixing weights pi (needs every N[k]).
+void constants_cluster(int k, int D, clusters_t* c);
+void mixing_weights(int K, clusters_t* c);
 
 // Seeding from global column sums (double): sum x, sum x^2 over all N events,
 // and the K seed rows (already gathered).  gaussian_kernel.cu:269-328,

