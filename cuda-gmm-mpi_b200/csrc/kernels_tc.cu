@@ -257,6 +257,7 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             // bank groups; the operand image puts the 4 K-chunks of an 8-row group next to each other
             // (LBO = 128, SBO = 512), so a warp stores 512 contiguous bytes: no bank conflicts either way.
             uint4 gh[2], gl[2];
+            float gdep = 0.0f;
 #pragma unroll
             for (int it2 = 0; it2 < 2; it2++) {
                 const int item = bt + it2 * 128;
@@ -266,6 +267,7 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 const float4 a = *reinterpret_cast<const float4*>(grow + (((2 * ce) ^ (k & 7)) << 4));
                 const float4 b = *reinterpret_cast<const float4*>(grow + (((2 * ce + 1) ^ (k & 7)) << 4));
                 float g[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                gdep += a.x + b.x;
                 if (GS) {
                     float hi[8], lo[8];
 #pragma unroll
@@ -282,14 +284,17 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     gh[it2] = make_uint4(pack_half2(g[0], g[1]), pack_half2(g[2], g[3]), pack_half2(g[4], g[5]), pack_half2(g[6], g[7]));
                 }
             }
-            // The raw tiles must BE in registers before the stage goes back to the TMA producer.  The plain LDS of z have
-            // no arithmetic consumer before the arrive, so the arrive is made data-dependent on every loaded value (a
-            // sum that is never NaN-compared true): the loads of the last dimensions otherwise raced with the refill.
-            float zdep = 0.0f;
+            // The raw tiles must BE in registers before the stage goes back to the TMA producer: an mbarrier arrive does
+            // not wait for the warp's outstanding LDS (measured: with nothing consuming the z loads before the arrive, the
+            // refill of the stage overtook the loads of the last dimensions).  The arrive is therefore made data-dependent
+            // on every load of this thread: one FADD chain over z and one component of each responsibility vector; the
+            // compared bit pattern (a signalling NaN) is never the result of an addition, whatever the data.
+            float dep = gdep;
 #pragma unroll
-            for (int d = 0; d < D; d++) zdep += z[d];
+            for (int d = 0; d < D; d++) dep += z[d];
+            const bool never = __float_as_uint(dep) == 0xff800001u;
             __syncwarp();
-            if (lane == 0 || zdep != zdep + 0.0f) mbar_arrive(&raw_empty[rs]);
+            if (lane == 0 || never) mbar_arrive(&raw_empty[rs]);
             mbar_wait_parked(&op_empty[os], oph ^ 1, 200);
             uint8_t* phi_hi = smem + C::OFF_PHI + os * C::PHI_STAGE;
             uint8_t* phi_lo = phi_hi + C::PHI_PART;
