@@ -92,6 +92,7 @@ struct gmm_ctx {
     float* d_memb = nullptr;
     size_t memb_pitch = 0;           // row pitch in floats (multiple of 32: TMA-aligned rows)
     float* d_memb_saved = nullptr;   // best configuration during gmm_fit
+    cudaEvent_t ev_stats = nullptr;  // statistics have reached the host
     // parameters
     float* d_epack = nullptr;    // SIMT E-step parameters [Kmax][epack_stride]
     float* h_epack = nullptr;    // pinned staging
@@ -326,7 +327,9 @@ static int reduce_stats_to_host(gmm_ctx* c, int K) {
     }
     timer_end(c, c->t_reduce);
     CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(double) * len, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev_stats, c->stream));
+    if (int rc = tc_mstep_cleanup(c->tc, c->stream)) return rc;     // runs while the host finalises
+    CUDA_TRY(cudaEventSynchronize(c->ev_stats));
     return GMM_OK;
 }
 
@@ -423,6 +426,7 @@ int gmm_create(gmm_ctx** out, int device, int n_local, int D, int Kmax, const fl
         }                                                                                            \
     } while (0)
     CREATE_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaEventCreateWithFlags(&c->ev_stats, cudaEventDisableTiming));
     const size_t nmax = n_local > 0 ? (size_t)n_local : 1;
     CREATE_TRY(cudaMalloc(&c->d_x_aos, sizeof(float) * nmax * D));
     c->memb_pitch = (nmax + 31) / 32 * 32;         // also the row pitch of the SoA event copy
@@ -480,6 +484,7 @@ void gmm_destroy(gmm_ctx* c) {
     cudaFree(c->d_epack); cudaFree(c->d_stats); cudaFree(c->d_shift);
     if (c->h_epack) cudaFreeHost(c->h_epack);
     if (c->h_stats) cudaFreeHost(c->h_stats);
+    if (c->ev_stats) cudaEventDestroy(c->ev_stats);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

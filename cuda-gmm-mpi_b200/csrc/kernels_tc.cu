@@ -381,15 +381,13 @@ __global__ void standardise_soa_kernel(const float* __restrict__ xs, float* __re
 }
 
 // Reduce the per-CTA FP32 partials in double, undo the operand scaling and write the packed statistics.
-__global__ void mstep_tc_finalize_kernel(const double* __restrict__ scratch, int ncta_x, int MT, int K, int D, int F,
-                                         const double* __restrict__ scale, double* __restrict__ stats) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= K * F) return;
-    const int k = idx / F, f = idx % F;
-    const int ty = k / kNCL, col = k % kNCL, mt = f / 128, row = f % 128;
-    double s = 0;
-    for (int cx = 0; cx < ncta_x; cx++)
-        s += scratch[(((size_t)(ty * ncta_x + cx) * MT + mt) * 128 + row) * kNCL + col];
+__global__ void __launch_bounds__(256)
+mstep_tc_finalize_kernel(const double* __restrict__ scratch, int ncta_x, int MT, int K, int D, int F,
+                         const double* __restrict__ scale, double* __restrict__ stats) {
+    // one block per feature row f; thread -> (cluster column, quarter of the CTAs): 512-byte coalesced reads
+    __shared__ double part[4][kNCL];
+    const int f = blockIdx.x, mt = f / 128, row = f % 128;
+    const int col = threadIdx.x & (kNCL - 1), q = threadIdx.x / kNCL;
     double fac = 1.0 / (double)kGammaScale;
     if (f >= 1 && f <= D) fac *= scale[f - 1];
     else if (f > D) {
@@ -397,7 +395,16 @@ __global__ void mstep_tc_finalize_kernel(const double* __restrict__ scratch, int
         const int i = tri_row(t), j = t - i * (i + 1) / 2;
         fac *= scale[i] * scale[j];
     }
-    stats[(size_t)k * F + f] += s * fac;
+    for (int ty = 0; ty * kNCL < K; ty++) {
+        double s = 0;
+        for (int cx = q; cx < ncta_x; cx += 4)
+            s += scratch[(((size_t)(ty * ncta_x + cx) * MT + mt) * 128 + row) * kNCL + col];
+        part[q][col] = s;
+        __syncthreads();
+        const int k = ty * kNCL + col;
+        if (q == 0 && k < K) stats[(size_t)k * F + f] += (part[0][col] + part[1][col] + part[2][col] + part[3][col]) * fac;
+        __syncthreads();
+    }
 }
 
 
@@ -756,6 +763,8 @@ struct TcState {
     double* d_scale = nullptr;       // [32] = 1 / inv_scale_f (double)
     double* d_scratch = nullptr;
     size_t scratch_floats = 0;
+    size_t scratch_clean_bytes = 0;  // leading bytes of d_scratch known to be zero
+    size_t scratch_dirty_bytes = 0;  // bytes the last M-step launch wrote
     bool have_shift = false;
     // E-step
     CUtensorMap tm_x128{};
@@ -1100,15 +1109,28 @@ static int launch_mstep_d(TcState* t, int K, double* d_stats, cudaStream_t strea
     const int gy = (K + kNCL - 1) / kNCL;
     if ((size_t)gx * gy * C::MT * 128 * kNCL > t->scratch_floats) return fail(GMM_ERR_STATE, "tensor M-step scratch too small");
     dim3 grid(gx, gy);
-    TC_CUDA_TRY(cudaMemsetAsync(t->d_scratch, 0, sizeof(double) * (size_t)gx * gy * C::MT * 128 * kNCL, stream));
+    // the flush warps add into zeroed per-CTA slots; tc_mstep_cleanup() zeroes the scratch after the statistics have
+    // left for the host (off the critical path), so only a launch that finds it dirty pays for a memset in front
+    const size_t scratch_bytes = sizeof(double) * (size_t)gx * gy * C::MT * 128 * kNCL;
+    if (t->scratch_clean_bytes < scratch_bytes) TC_CUDA_TRY(cudaMemsetAsync(t->d_scratch, 0, scratch_bytes, stream));
     if (t->gamma_split)
         mstep_tc_kernel<D, true><<<grid, kMThreads, C::SMEM_BYTES, stream>>>(t->tm_x, t->tm_g, t->n, t->d_scratch, per);
     else
         mstep_tc_kernel<D, false><<<grid, kMThreads, C::SMEM_BYTES, stream>>>(t->tm_x, t->tm_g, t->n, t->d_scratch, per);
     TC_CUDA_TRY(cudaGetLastError());
     const int F = C::F;
-    mstep_tc_finalize_kernel<<<(K * F + 255) / 256, 256, 0, stream>>>(t->d_scratch, gx, C::MT, K, D, F, t->d_scale, d_stats);
+    mstep_tc_finalize_kernel<<<F, 256, 0, stream>>>(t->d_scratch, gx, C::MT, K, D, F, t->d_scale, d_stats);
     TC_CUDA_TRY(cudaGetLastError());
+    t->scratch_dirty_bytes = scratch_bytes;
+    t->scratch_clean_bytes = 0;
+    return GMM_OK;
+}
+
+int tc_mstep_cleanup(TcState* t, cudaStream_t stream) {
+    if (!t || !t->d_scratch || t->scratch_dirty_bytes == 0) return GMM_OK;
+    TC_CUDA_TRY(cudaMemsetAsync(t->d_scratch, 0, t->scratch_dirty_bytes, stream));
+    t->scratch_clean_bytes = t->scratch_dirty_bytes;
+    t->scratch_dirty_bytes = 0;
     return GMM_OK;
 }
 

@@ -33,5 +33,8 @@ int  tc_params_commit(TcState*, int K, int bad, cudaStream_t stream);
 int  tc_launch_estep(TcState*, int K, double* d_ll, cudaStream_t stream);
 // Accumulates sum_n g[k][n] * phi_f(x_n - shift) into d_stats[k*F + f] (double, original units).
 int  tc_launch_mstep(TcState*, int K, double* d_stats, cudaStream_t stream);
+// Zeroes the per-CTA scratch of the last tc_launch_mstep for the next one; meant to be enqueued behind the D2H copy
+// of the statistics so that it runs while the host finalises.
+int  tc_mstep_cleanup(TcState*, cudaStream_t stream);
 
 }  // namespace gmm
