@@ -60,7 +60,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -70,14 +70,27 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def wait_ready(self, timeout=5.0):
+        t_end = time.time() + timeout
+        while self.proc and not self.lines and time.time() < t_end:
+            time.sleep(0.01)
+
+    def mark(self):
+        """Index of the next sample: brackets the timed region (the process is started well before it, so that
+        its fork/exec and NVML start-up do not run inside the region)."""
+        return len(self.lines)
+
+    def stop(self, begin=0, end=None):
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         self.t.join(timeout=2)
+        lines = self.lines[begin:(end + 1 if end is not None else None)]
+        if not lines:                                   # region shorter than one sampling period: nearest sample
+            lines = self.lines[max(0, begin - 1):begin + 1] or self.lines[-1:]
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -206,12 +219,15 @@ def main():
     eng = make_engine()
     seeded = eng.seed(K)
     eng.estep(K)                                         # initial E-step (gaussian.cu:487-523)
-    eng.em_iterations(K, args.warmup)
-    eng.profile(reset=True)
     sampler = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
-        sampler.start()
+        sampler.start()                                  # before the warm-up: start-up cost stays outside the timed region
+    eng.em_iterations(K, args.warmup)
+    if rank == 0:
+        sampler.wait_ready()
+    eng.profile(reset=True)
+    barrier()
+    m0 = sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     t0 = time.perf_counter()
@@ -220,8 +236,9 @@ def main():
     torch.cuda.synchronize()
     dt_wall = time.perf_counter() - t0
     dt = ev0.elapsed_time(ev1) * 1e-3                    # device clock around the region (the engine syncs its stream before returning)
+    m1 = sampler.mark()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(m0, m1) if rank == 0 else None
     dt = max_over_ranks(dt)
     prof = eng.profile()
     value = args.steps / dt
