@@ -190,7 +190,7 @@ static int ensure_moments(gmm_ctx* c);
 // with_constants: the inverse / constant / pi of every cluster still have to be derived from R (M-step
 // finalisation).  On the tensor path that work shares ONE parallel loop over the clusters with the E-step
 // operand (Cholesky + FP16 split): one thread-team wake-up per EM iteration instead of two.
-static int upload_params(gmm_ctx* c, int K, bool with_constants = false) {
+static int upload_params(gmm_ctx* c, int K, bool with_constants = false, bool with_finalize = false) {
     if (int rc = check_path(c, K)) return rc;
     auto t0 = std::chrono::steady_clock::now();
     c->estep_tensor_ready = false;
@@ -198,17 +198,20 @@ static int upload_params(gmm_ctx* c, int K, bool with_constants = false) {
         if (int rc = ensure_moments(c)) return rc;
         int rc = tc_params_begin(c->tc, K, c->stream);
         if (rc == GMM_OK) {
+            if (with_finalize)                     // pi needs every N[k] = (float)S0 before the per-cluster loop
+                for (int k = 0; k < K; k++) c->host.N[k] = (float)c->h_stats[(size_t)k * c->F];
             if (with_constants) mixing_weights(K, &c->host);
             const int kp = tc_params_padded(c->tc, K), nt = c->host_threads, D = c->D;
             int bad = 0;
             (void)nt;
 #pragma omp parallel for schedule(static) num_threads(nt) reduction(max : bad) if (nt > 1 && K >= 8)
             for (int k = 0; k < kp; k++) {
+                if (with_finalize && k < K) finalize_cluster(c->h_stats, c->shift, k, D, &c->host);
                 if (with_constants && k < K) constants_cluster(k, D, &c->host);
                 const int b = tc_params_cluster(c->tc, &c->host, k, K);
                 bad = b > bad ? b : bad;
             }
-            with_constants = false;
+            with_constants = with_finalize = false;
             rc = tc_params_commit(c->tc, K, bad, c->stream);
         }
         if (rc == GMM_OK) c->estep_tensor_ready = true;
@@ -216,6 +219,7 @@ static int upload_params(gmm_ctx* c, int K, bool with_constants = false) {
         // GMM_ERR_STATE under GMM_PATH_AUTO: a cluster whose inverse covariance is not positive definite
         // (or does not fit FP16) — this parameter set is evaluated by the FP32 SIMT kernel instead.
     }
+    if (with_finalize) finalize_from_stats(c->h_stats, c->shift, K, c->D, &c->host, c->host_threads, /*with_constants=*/false);
     if (with_constants) constants_from_R(K, c->D, &c->host, c->host_threads);
     if (!c->estep_tensor_ready) {
         build_epack(K, c->D, &c->host, c->h_epack);
@@ -336,10 +340,9 @@ static int reduce_stats_to_host(gmm_ctx* c, int K) {
 }
 
 static int finalize_and_upload(gmm_ctx* c, int K) {
-    auto t0 = std::chrono::steady_clock::now();
-    finalize_from_stats(c->h_stats, c->shift, K, c->D, &c->host, c->host_threads, /*with_constants=*/false);
-    c->host_const_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    return upload_params(c, K, /*with_constants=*/true);   // inverse, constants, pi + E-step operand (timed as "upload")
+    // N, means, R (gaussian.cu:611-622, 663-679), inverse + constants + pi (:698-708) and the E-step operand: on the
+    // tensor path ONE parallel loop over the clusters (timed as "upload"), else the serial + parallel pieces
+    return upload_params(c, K, /*with_constants=*/true, /*with_finalize=*/true);
 }
 
 // Global column moments (sum x, sum x^2 over ALL events of all ranks), computed once per

@@ -97,36 +97,38 @@ void constants_from_R(int K, int D, clusters_t* c, int num_threads) {
 // BEFORE the division).  Input statistics are taken about `shift`:
 //   S0 = sum g, S1 = sum g (x - shift), S2 = sum g (x - shift)(x - shift)^T
 // so that  sum g (x - mu)(x - mu)^T = S2 - S1 S1^T / S0  with mu = shift + S1/S0.
+void finalize_cluster(const double* stats, const double* shift, int k, int D, clusters_t* c) {
+    const int F = num_features(D);
+    const double* s = stats + (size_t)k * F;
+    const double S0 = s[0];
+    const float Nf = (float)S0;
+    c->N[k] = Nf;
+    float* mu = c->means + (size_t)k * D;
+    float* R = c->R + (size_t)k * D * D;
+    double m[GMM_MAX_DIMENSIONS];
+    for (int d = 0; d < D; d++) {
+        m[d] = (S0 != 0.0) ? s[1 + d] / S0 : 0.0;
+        mu[d] = (Nf > 0.5f) ? (float)(m[d] + shift[d]) : 0.0f;              // gaussian.cu:614-618
+    }
+    if (Nf > 0.5f) {
+        const double inv = 1.0 / (double)Nf;
+        for (int i = 0; i < D; i++)
+            for (int j = 0; j <= i; j++) {
+                double cov = (Nf >= 1.0f) ? s[feat2(D, i, j)] - m[i] * s[1 + j] : 0.0;   // kernel :658-668
+                if (i == j) cov += c->avgvar[k];                                      // kernel :673-675
+                const float v = (float)(cov * inv);                                   // gaussian.cu:664-667
+                R[i * D + j] = v;
+                R[j * D + i] = v;
+            }
+    } else {                                                                          // gaussian.cu:668-677
+        for (int i = 0; i < D; i++)
+            for (int j = 0; j < D; j++) R[i * D + j] = (i == j) ? 1.0f : 0.0f;
+    }
+}
+
 void finalize_from_stats(const double* stats, const double* shift, int K, int D, clusters_t* c,
                          int num_threads, bool with_constants) {
-    const int F = num_features(D);
-    for (int k = 0; k < K; k++) {
-        const double* s = stats + (size_t)k * F;
-        const double S0 = s[0];
-        const float Nf = (float)S0;
-        c->N[k] = Nf;
-        float* mu = c->means + (size_t)k * D;
-        float* R = c->R + (size_t)k * D * D;
-        double m[GMM_MAX_DIMENSIONS];
-        for (int d = 0; d < D; d++) {
-            m[d] = (S0 != 0.0) ? s[1 + d] / S0 : 0.0;
-            mu[d] = (Nf > 0.5f) ? (float)(m[d] + shift[d]) : 0.0f;              // gaussian.cu:614-618
-        }
-        if (Nf > 0.5f) {
-            const double inv = 1.0 / (double)Nf;
-            for (int i = 0; i < D; i++)
-                for (int j = 0; j <= i; j++) {
-                    double cov = (Nf >= 1.0f) ? s[feat2(D, i, j)] - m[i] * s[1 + j] : 0.0;   // kernel :658-668
-                    if (i == j) cov += c->avgvar[k];                                      // kernel :673-675
-                    const float v = (float)(cov * inv);                                   // gaussian.cu:664-667
-                    R[i * D + j] = v;
-                    R[j * D + i] = v;
-                }
-        } else {                                                                          // gaussian.cu:668-677
-            for (int i = 0; i < D; i++)
-                for (int j = 0; j < D; j++) R[i * D + j] = (i == j) ? 1.0f : 0.0f;
-        }
-    }
+    for (int k = 0; k < K; k++) finalize_cluster(stats, shift, k, D, c);
     if (with_constants) constants_from_R(K, D, c, num_threads);
 }
 

@@ -31,6 +31,8 @@ void constants_from_R(int K, int D, clusters_t* c, int num_threads);
 // The two parts of constants_from_R, for callers that run their own loop over the clusters:
 // inverse + constant of one cluster, and the mixing weights pi (needs every N[k]).
 void constants_cluster(int k, int D, clusters_t* c);
+// N, mean and covariance of ONE cluster from the packed statistics (the loop body of finalize_from_stats).
+void finalize_cluster(const double* stats, const double* shift, int k, int D, clusters_t* c);
 void mixing_weights(int K, clusters_t* c);
 
 // Seeding from global column sums (double): sum x, sum x^2 over all N events,

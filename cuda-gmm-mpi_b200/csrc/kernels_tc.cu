@@ -772,6 +772,10 @@ struct TcState {
     uint8_t* d_bimg = nullptr;       // [MAXNG * B_GROUP] resident B operand image
     uint8_t* h_bimg = nullptr;       // pinned
     size_t bimg_bytes = 0;
+    uint8_t* d_opnd = nullptr;       // [ck (e_ck_len floats) | B image]; d_ck / d_bimg point into it
+    uint8_t* h_opnd = nullptr;       // pinned mirror
+    cudaEvent_t ev_h2d = nullptr;    // the last operand copy has left the pinned buffer
+    bool h2d_pending = false;
     float* d_ck = nullptr;           // [e_ck_len]
     float* h_ck = nullptr;           // pinned [e_ck_len]
     float* d_den = nullptr;          // [passes][memb_pitch] per-pass log-denominators (Kmax > 64 only)
@@ -842,10 +846,15 @@ int tc_create(TcState** out, const float* d_x_aos, const float* d_x_soa, int n, 
         const int passes = (Kmax + 63) / 64;
         t->e_ck_len = passes * 64;
         t->bimg_bytes = (size_t)passes * pass_bytes_for(D);
-        TC_CUDA_TRY(cudaMalloc(&t->d_bimg, t->bimg_bytes));
-        TC_CUDA_TRY(cudaMallocHost(&t->h_bimg, t->bimg_bytes));
-        TC_CUDA_TRY(cudaMalloc(&t->d_ck, sizeof(float) * t->e_ck_len));
-        TC_CUDA_TRY(cudaMallocHost(&t->h_ck, sizeof(float) * t->e_ck_len));
+        // one staging / device buffer [ck | B image]: the operand of an iteration travels in ONE H2D copy
+        const size_t ck_bytes = sizeof(float) * t->e_ck_len;         // 256 B per pass: keeps the image 16-byte aligned
+        TC_CUDA_TRY(cudaMalloc(&t->d_opnd, ck_bytes + t->bimg_bytes));
+        TC_CUDA_TRY(cudaMallocHost(&t->h_opnd, ck_bytes + t->bimg_bytes));
+        t->d_ck = reinterpret_cast<float*>(t->d_opnd);
+        t->h_ck = reinterpret_cast<float*>(t->h_opnd);
+        t->d_bimg = t->d_opnd + ck_bytes;
+        t->h_bimg = t->h_opnd + ck_bytes;
+        TC_CUDA_TRY(cudaEventCreateWithFlags(&t->ev_h2d, cudaEventDisableTiming));
         if (passes > 1) TC_CUDA_TRY(cudaMalloc(&t->d_den, sizeof(float) * (size_t)passes * memb_pitch));
         t->emap_ok = true;
     }
@@ -862,9 +871,9 @@ void tc_set_gamma_split(TcState* t, bool on) { if (t) t->gamma_split = on; }
 void tc_destroy(TcState* t) {
     if (!t) return;
     cudaFree(t->d_shift_f); cudaFree(t->d_inv_scale_f); cudaFree(t->d_scale); cudaFree(t->d_scratch);
-    cudaFree(t->d_bimg); cudaFree(t->d_ck); cudaFree(t->d_den); cudaFree(t->d_z_soa);
-    if (t->h_bimg) cudaFreeHost(t->h_bimg);
-    if (t->h_ck) cudaFreeHost(t->h_ck);
+    cudaFree(t->d_opnd); cudaFree(t->d_den); cudaFree(t->d_z_soa);
+    if (t->h_opnd) cudaFreeHost(t->h_opnd);
+    if (t->ev_h2d) cudaEventDestroy(t->ev_h2d);
     delete t;
 }
 
@@ -1018,7 +1027,11 @@ static int bimg_cluster_any(TcState* t, const clusters_t* host, int k, int K) {
 int tc_params_begin(TcState* t, int K, cudaStream_t stream) {
     if (!t || !t->emap_ok) return fail(GMM_ERR_STATE, "tensor E-step not initialised for this shape");
     if (!t->have_shift) return fail(GMM_ERR_STATE, "tensor E-step needs the global moments (shift/scale) first");
-    TC_CUDA_TRY(cudaStreamSynchronize(stream));          // the pinned staging buffers may still be in flight
+    (void)stream;
+    if (t->h2d_pending) {                                // the previous copy out of the pinned buffer must have finished
+        TC_CUDA_TRY(cudaEventSynchronize(t->ev_h2d));
+        t->h2d_pending = false;
+    }
     for (int k = K; k < t->e_ck_len; k++) t->h_ck[k] = -1e30f;
     return GMM_OK;
 }
@@ -1031,8 +1044,9 @@ int tc_params_commit(TcState* t, int K, int bad, cudaStream_t stream) {
     t->e_NG = (K + 15) / 16;
     // only the supergroups in use travel (the image is contiguous per supergroup; 4 supergroups = 64 clusters)
     const size_t used = (size_t)t->e_NG * (pass_bytes_for(t->D) / 4);
-    TC_CUDA_TRY(cudaMemcpyAsync(t->d_bimg, t->h_bimg, used, cudaMemcpyHostToDevice, stream));
-    TC_CUDA_TRY(cudaMemcpyAsync(t->d_ck, t->h_ck, sizeof(float) * t->e_ck_len, cudaMemcpyHostToDevice, stream));
+    TC_CUDA_TRY(cudaMemcpyAsync(t->d_opnd, t->h_opnd, sizeof(float) * t->e_ck_len + used, cudaMemcpyHostToDevice, stream));
+    TC_CUDA_TRY(cudaEventRecord(t->ev_h2d, stream));
+    t->h2d_pending = true;
     return GMM_OK;
 }
 
