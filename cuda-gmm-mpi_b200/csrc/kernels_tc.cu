@@ -12,16 +12,18 @@
 // (hi*hi, lo*hi, hi*lo) are accumulated, i.e. 3 MMA passes at FP16 rate.
 //
 // Dataflow per CTA (persistent over a contiguous range of events, 512 threads):
-//   warp 0      TMA producer: raw event tile [32][D] and raw responsibility tile
-//               [64 clusters][32 events] (2-D tensor maps, zero fill out of bounds)
-//   warps 4-11  operand builders: centre/scale, form the products, split hi/lo,
-//               write the UMMA operand images (SWIZZLE_NONE core-matrix layout)
+//   warp 0      TMA producer: tile [D][32 events] of the pre-standardised SoA copy z and raw
+//               responsibility tile [64 clusters][32 events] (2-D tensor maps, SWIZZLE_128B for
+//               the latter, zero fill out of bounds)
+//   warps 4-11  operand builders (two warpgroups on alternate tiles): form the products, split
+//               hi/lo, write the UMMA operand images (SWIZZLE_NONE core-matrix layout)
 //   warp 1      MMA issuer: 3 x 2 x MT tcgen05.mma (M=128, N=64, K=16) per 32 events
 //   warps 12-15 flush: every 128 events the TMEM accumulators are added (FP32, round to
 //               nearest) into register-resident partial sums (setmaxnreg gives this
 //               warpgroup 240 registers) — the TMEM accumulation itself truncates:
 //               measured bias -1e-7 per MMA step (profiles/tc_probe_r1.txt), so the
-//               chains are kept to 24 steps
+//               chains are kept to 24 steps; every 2048 events the partial sums move into
+//               per-thread double slots of an L2-resident scratch (RED.ADD.F64)
 // A second tiny kernel reduces the per-CTA partials in double and un-scales.
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -426,12 +428,14 @@ mstep_tc_finalize_kernel(const double* __restrict__ scratch, int ncta_x, int MT,
 // only the event tiles stream.
 //
 // One persistent CTA per SM, 512 threads:
-//   warp 1      MMA issuer: per 128-event tile NG groups x KSTEPS tcgen05.mma (M=128, N=G*D)
-//   warp 2      TMEM allocation
+//   warp 1      MMA issuer: per 128-event tile, per supergroup of 16 clusters and per block c of 8
+//               output dimensions, the k-steps that block needs (tcgen05.mma M=128, N=128, K=16)
+//   warp 2      TMEM allocation (4 accumulator buffers x 128 columns)
 //   warps 4-7   converters: coalesced loads of the event rows, centre/scale, FP16 hi/lo
 //               split, K-major SWIZZLE_NONE operand image (2 stages)
-//   warps 8-15  epilogue (two warpgroups, each takes half of the clusters of every group):
-//               tcgen05.ld -> squares -> logits -> online max / sum-exp -> responsibilities
+//   warps 8-15  epilogue (two warpgroups, each takes 8 of the 16 clusters of every supergroup):
+//               tcgen05.ld -> packed squares, carried over the blocks -> base-2 logits ->
+//               max / sum-exp2 (+ exchange between the warpgroups) -> responsibilities
 //               (coalesced 128-byte row segments) + log-likelihood (double)
 // ===========================================================================
 constexpr int kEThreads = 512;
@@ -906,8 +910,10 @@ int tc_set_shift_scale(TcState* t, double* shift, const double* scale, cudaStrea
 // Host side of the tensor E-step operand: per cluster the upper-triangular factor W of
 // Rinv = W^T W (Cholesky of the symmetrised inverse covariance, double), expressed in the
 // centred/scaled coordinates of the kernel, FP16 hi/lo split, laid out as the resident
-// K-major B image of each CTA of the pair.  Fails (GMM_ERR_STATE) when Rinv is not positive
-// definite or the factor overflows FP16; the caller then uses the SIMT kernel for this state.
+// K-major B image ([supergroup][block][chunk][128 rows][16 B]).  Fails (GMM_ERR_STATE) when Rinv
+// is not positive definite or the factor overflows FP16; the caller then uses the SIMT kernel
+// for this state.
+
 // float -> IEEE half bits, round to nearest even (normal, subnormal and zero; callers check the range)
 static inline uint16_t f2h_bits(float f) {
     uint32_t x;
