@@ -315,7 +315,9 @@ static int run_estep(gmm_ctx* c, int K) {
 // M-step accumulation of the local statistics into stats[0 .. K*F).
 static int run_mstep_accumulate(gmm_ctx* c, int K) {
     timer_begin(c, c->t_mstep);
-    int rc = use_tensor_mstep(c, K) ? tc_launch_mstep(c->tc, K, c->d_stats, c->stream)
+    float min_nk = INFINITY;                       // cluster sizes of the parameters the responsibilities came from
+    for (int k = 0; k < K; k++) min_nk = std::fmin(min_nk, c->host.N[k]);
+    int rc = use_tensor_mstep(c, K) ? tc_launch_mstep(c->tc, K, c->d_stats, c->stream, min_nk)
                                     : launch_mstep_simt(c, K);
     timer_end(c, c->t_mstep);
     return rc;
@@ -541,7 +543,7 @@ int gmm_set_option(gmm_ctx* c, const char* key, double value) {
         c->host_threads_fixed = true;
         tc_set_host_threads(c->tc, c->host_threads);
     }
-    else if (k == "mstep_gamma_split") { tc_set_gamma_split(c->tc, value != 0); }
+    else if (k == "mstep_gamma_split") { tc_set_gamma_split(c->tc, (int)value); }
     else if (k == "write_memberships") { /* accepted; every E-step materialises memberships in this build */ }
     else return fail(GMM_ERR_ARG, "gmm_set_option: unknown key '" + k + "'");
     return GMM_OK;

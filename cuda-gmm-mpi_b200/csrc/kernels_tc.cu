@@ -786,7 +786,7 @@ struct TcState {
     int e_ck_len = 0;                // Kmax rounded up to whole passes of 64
     int e_NG = 0;
     int host_threads = 8;
-    bool gamma_split = true;         // M-step: FP16 hi/lo pair for the responsibilities (see mstep_tc_kernel)
+    int gamma_split = 2;             // M-step: FP16 hi/lo pair for the responsibilities: 0 never, 1 always, 2 by cluster size
     double h_shift[GMM_MAX_DIMENSIONS] = {0}, h_scale[GMM_MAX_DIMENSIONS] = {0};
 };
 
@@ -870,7 +870,7 @@ int tc_create(TcState** out, const float* d_x_aos, const float* d_x_soa, int n, 
 }
 
 void tc_set_host_threads(TcState* t, int n) { if (t) t->host_threads = n < 1 ? 1 : n; }
-void tc_set_gamma_split(TcState* t, bool on) { if (t) t->gamma_split = on; }
+void tc_set_gamma_split(TcState* t, int mode) { if (t) t->gamma_split = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 
 void tc_destroy(TcState* t) {
     if (!t) return;
@@ -1111,8 +1111,13 @@ int tc_launch_estep(TcState* t, int K, double* d_ll, cudaStream_t stream) {
     }
 }
 
+// Clusters of at least this many (soft) events take the single-FP16 responsibilities under mode 2: the rounding is an
+// unbiased relative perturbation <= 2^-12 per weight, so the statistics of a cluster move by ~1.4e-4 / sqrt(n_eff),
+// n_eff >= N_k: below 3.1e-6 from here on (30x under the parity bar, the size of the FP32 noise already there).
+constexpr float kGammaSplitMinN = 2048.0f;
+
 template <int D>
-static int launch_mstep_d(TcState* t, int K, double* d_stats, cudaStream_t stream) {
+static int launch_mstep_d(TcState* t, int K, double* d_stats, cudaStream_t stream, float min_nk) {
     using C = MCfg<D>;
     static_assert(C::SMEM_BYTES <= 232448, "shared memory budget");
     static_assert(C::TMEM_COLS <= 512, "TMEM budget");
@@ -1133,7 +1138,8 @@ static int launch_mstep_d(TcState* t, int K, double* d_stats, cudaStream_t strea
     // left for the host (off the critical path), so only a launch that finds it dirty pays for a memset in front
     const size_t scratch_bytes = sizeof(double) * (size_t)gx * gy * C::MT * 128 * kNCL;
     if (t->scratch_clean_bytes < scratch_bytes) TC_CUDA_TRY(cudaMemsetAsync(t->d_scratch, 0, scratch_bytes, stream));
-    if (t->gamma_split)
+    const bool split = t->gamma_split == 1 || (t->gamma_split == 2 && !(min_nk >= kGammaSplitMinN));
+    if (split)
         mstep_tc_kernel<D, true><<<grid, kMThreads, C::SMEM_BYTES, stream>>>(t->tm_x, t->tm_g, t->n, t->d_scratch, per);
     else
         mstep_tc_kernel<D, false><<<grid, kMThreads, C::SMEM_BYTES, stream>>>(t->tm_x, t->tm_g, t->n, t->d_scratch, per);
@@ -1154,16 +1160,16 @@ int tc_mstep_cleanup(TcState* t, cudaStream_t stream) {
     return GMM_OK;
 }
 
-int tc_launch_mstep(TcState* t, int K, double* d_stats, cudaStream_t stream) {
+int tc_launch_mstep(TcState* t, int K, double* d_stats, cudaStream_t stream, float min_nk) {
     if (!t || !t->maps_ok) return fail(GMM_ERR_STATE, "tensor-core M-step not initialised for this shape");
     if (!t->have_shift) return fail(GMM_ERR_STATE, "tensor-core M-step needs gmm_seed (shift/scale) first");
     switch (t->D) {
-        case 4: return launch_mstep_d<4>(t, K, d_stats, stream);
-        case 8: return launch_mstep_d<8>(t, K, d_stats, stream);
-        case 12: return launch_mstep_d<12>(t, K, d_stats, stream);
-        case 16: return launch_mstep_d<16>(t, K, d_stats, stream);
-        case 20: return launch_mstep_d<20>(t, K, d_stats, stream);
-        case 24: return launch_mstep_d<24>(t, K, d_stats, stream);
+        case 4: return launch_mstep_d<4>(t, K, d_stats, stream, min_nk);
+        case 8: return launch_mstep_d<8>(t, K, d_stats, stream, min_nk);
+        case 12: return launch_mstep_d<12>(t, K, d_stats, stream, min_nk);
+        case 16: return launch_mstep_d<16>(t, K, d_stats, stream, min_nk);
+        case 20: return launch_mstep_d<20>(t, K, d_stats, stream, min_nk);
+        case 24: return launch_mstep_d<24>(t, K, d_stats, stream, min_nk);
         default: return fail(GMM_ERR_ARG, "tensor-core M-step: unsupported D");
     }
 }

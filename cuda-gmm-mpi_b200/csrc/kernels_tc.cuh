@@ -17,8 +17,9 @@ int  tc_create(TcState** out, const float* d_x_aos, const float* d_x_soa, int n,
                int num_sms, cudaStream_t stream);
 void tc_destroy(TcState*);
 void tc_set_host_threads(TcState*, int n);
-// M-step responsibilities as an FP16 hi/lo pair (true, default) or one round-to-nearest FP16 value (false).
-void tc_set_gamma_split(TcState*, bool on);
+// M-step responsibilities as an FP16 hi/lo pair (1), as one round-to-nearest FP16 value (0), or chosen per launch
+// from the smallest cluster size the caller passes to tc_launch_mstep (2, default: pair below 2048 events).
+void tc_set_gamma_split(TcState*, int mode);
 // Centre/scale used inside the tensor kernels: z = (x - shift) * inv_scale, both rounded to
 // float; `shift` is updated in place to the float-rounded values actually used.
 int  tc_set_shift_scale(TcState*, double* shift, const double* scale, cudaStream_t stream);
@@ -32,7 +33,8 @@ int  tc_params_cluster(TcState*, const clusters_t* host, int k, int K);
 int  tc_params_commit(TcState*, int K, int bad, cudaStream_t stream);
 int  tc_launch_estep(TcState*, int K, double* d_ll, cudaStream_t stream);
 // Accumulates sum_n g[k][n] * phi_f(x_n - shift) into d_stats[k*F + f] (double, original units).
-int  tc_launch_mstep(TcState*, int K, double* d_stats, cudaStream_t stream);
+// min_nk: smallest N_k of the current parameters (global, all ranks); only read under gamma-split mode 2.
+int  tc_launch_mstep(TcState*, int K, double* d_stats, cudaStream_t stream, float min_nk);
 // Zeroes the per-CTA scratch of the last tc_launch_mstep for the next one; meant to be enqueued behind the D2H copy
 // of the statistics so that it runs while the host finalises.
 int  tc_mstep_cleanup(TcState*, cudaStream_t stream);

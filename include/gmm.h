@@ -100,9 +100,10 @@ int  gmm_comm_rank(const gmm_ctx*, int* rank, int* nranks);
  * "write_memberships" (1 = every E-step materialises memberships, as the
  * reference does; 0 = only gmm_estep()/gmm_get_clusters() do),
  * "host_threads" (threads of the host-side finalisation),
- * "mstep_gamma_split" (tensor M-step: 1 (default) = responsibilities enter
- * the MMA as an FP16 hi/lo pair, 0 = one round-to-nearest FP16 value:
- * 10 % faster kernel, 1e-4/sqrt(n_k) statistical error per cluster).      */
+ * "mstep_gamma_split" (tensor M-step: 1 = responsibilities enter the MMA as
+ * an FP16 hi/lo pair, 0 = as one round-to-nearest FP16 value (10 % faster
+ * kernel, ~1.4e-4/sqrt(N_k) statistical error per cluster), 2 (default) =
+ * pair whenever a cluster has fewer than 2048 events).                    */
 int  gmm_set_option(gmm_ctx*, const char* key, double value);
 
 /* ---- operators (one per reference kernel group) ------------------------- */

@@ -156,6 +156,31 @@ def test_mstep_tensor_path_large(loaded, oracle64, N, D, K):
     assert_params_close(got, ref, K)
 
 
+@pytest.mark.parametrize("mode", [2, 0, 1])
+def test_mstep_tensor_gamma_modes_large_clusters(loaded, oracle64, mode):
+    """Tensor M-step with clusters of 50k-180k events: mode 2 (default) picks the single-FP16 responsibilities here
+    (every N_k >= 2048), mode 0 forces them, mode 1 forces the hi/lo pair — all inside the per-call 1e-4 bar."""
+    pkg = loaded
+    N, D, K = 400_000, 24, 3
+    ev = pkg.synth.make_blobs(N, D, K, seed=808)
+    ref = fitted_params(pkg, oracle64, ev, K, iters=2)
+    assert ref.N.min() >= 2048
+    soa = oracle64.transpose(ev)
+    with pkg.Engine(ev, K) as eng:
+        eng.set_option("path", pkg.PATH_TENSOR)
+        eng.set_option("mstep_gamma_split", mode)
+        eng.seed(K)
+        eng.set_clusters(K, ref)
+        eng.estep(K)
+        eng.mstep(K)
+        eng.constants(K)
+        got = eng.get_clusters(K)
+    oracle64.estep(soa, ref, K)
+    oracle64.mstep(soa, ref, K)
+    oracle64.constants(ref, K)
+    assert_params_close(got, ref, K)
+
+
 @pytest.mark.parametrize("path", PATHS)
 def test_seed_parity(loaded, oracle64, path):
     pkg = loaded
