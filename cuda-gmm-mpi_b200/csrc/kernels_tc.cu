@@ -35,6 +35,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -468,7 +469,11 @@ template <int D> struct ECfg {
     static_assert(LPT == 32, "logits per thread");
 };
 
-template <int D>
+// ALT = false: both epilogue warpgroups work on every tile (each takes 8 of the 16 clusters of a supergroup and they
+// exchange (max, sum) through shared memory).  ALT = true (experimental, GMM_ESTEP_ALT=1): the warpgroups take alternate
+// tiles and each handles all 16 clusters — no exchange, and the log-sum-exp / store phase of one tile overlaps the
+// accumulator reads of the next, so the MMA issuer is not held up by full TMEM buffers during that phase.
+template <int D, bool ALT>
 __global__ void __launch_bounds__(kEThreads, 1)
 estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_img, const float* __restrict__ ck,
                 const float* __restrict__ shift_f, const float* __restrict__ inv_scale_f, float* __restrict__ memb,
@@ -485,6 +490,9 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
     uint64_t* acc_full = bars + 5;      // [NBUF]  tcgen05.commit
     uint64_t* acc_empty = bars + 5 + C::NBUF;     // [NBUF]  8 epilogue warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * C::NBUF);
+    // ALT: the odd tiles' accumulators are announced on a second set of barriers, so that each epilogue warpgroup only
+    // ever waits for the NEXT phase of a barrier (a parity wait cannot tell phase p from phase p + 2)
+    uint64_t* acc_full_odd = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR + 384);   // [NBUF]
     float* ck_s = reinterpret_cast<float*>(smem + C::OFF_CK);
     float2* ex = reinterpret_cast<float2*>(smem + C::OFF_EX);
     float* sh_s = reinterpret_cast<float*>(smem + C::OFF_BAR + 128);   // [32] shift, [32] inverse scale
@@ -496,8 +504,9 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; s++) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < C::NBUF; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
+        for (int s = 0; s < C::NBUF; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], ALT ? 4 : 8); }
         mbar_init(b_full, 1);
+        if (ALT) for (int s = 0; s < C::NBUF; s++) mbar_init(&acc_full_odd[s], 1);
         fence_mbar_init();
     }
     if (threadIdx.x < 64) ck_s[threadIdx.x] = ck[threadIdx.x] * 1.4426950408889634f;   // base-2 logits in the epilogue
@@ -516,7 +525,8 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
 
     // register re-partition inside the CTA's launch allocation (512 x 128): WG0 40, converters 72, epilogue 2 x 200
     if (warp < 4) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      if constexpr (ALT) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+      else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
       if (warp == 1) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
@@ -552,7 +562,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                                 acc = true;
                             }
                         }
-                        mma_commit(&acc_full[buf]);
+                        mma_commit(ALT && (it & 1) ? &acc_full_odd[buf] : &acc_full[buf]);
                         buf = (buf + 1) % C::NBUF;
                     }
                 }
@@ -561,7 +571,8 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
         }
       }
     } else if (warp < 8) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+        if constexpr (ALT) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
         // ===================== converters =====================
         const int row = threadIdx.x - 128;
         for (int it = 0; it < my_tiles; it++) {
@@ -607,8 +618,104 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
             if (lane == 0) mbar_arrive(&a_full[st]);
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        if constexpr (ALT) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");   // 128 x (32 + 64 + 2 x 208) = 64K registers
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
         // ===================== epilogue =====================
+      if constexpr (ALT) {
+        // warpgroup g takes the tiles it = g, g+2, ...; thread = event row, all clusters of the pass in this thread
+        const int g = (warp - 8) >> 2, q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const int NB = NSG * C::CP;                            // blocks per tile; buffer of block j: j % NBUF (restarts per tile)
+        constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+        double ll_acc = 0.0;
+        for (int it = g; it < my_tiles; it += 2) {
+            const long long e = (long long)((int)blockIdx.x + it * (int)gridDim.x) * 128 + row;
+            uint32_t pf[C::NBUF];                              // parity of acc_full[b] at its first use in this tile
+#pragma unroll
+            for (int b = 0; b < C::NBUF; b++) {
+                const int uses = b < NB ? (NB - b + C::NBUF - 1) / C::NBUF : 0;   // uses of buffer b per tile
+                pf[b] = (uint32_t)((it >> 1) * uses) & 1u;     // this warpgroup's own barrier set: its (it / 2)-th tile
+            }
+            float lg[C::MAXSG * C::GB];                        // base-2 logits of all clusters of the pass
+            float mx = -INFINITY;
+#pragma unroll
+            for (int sg = 0; sg < C::MAXSG; sg++) {
+                if (sg < NSG) {
+                    uint64_t qs[C::GB];                        // packed partial sums of squares, one pair per cluster
+#pragma unroll
+                    for (int i = 0; i < C::GB; i++) qs[i] = 0ull;
+#pragma unroll
+                    for (int c = 0; c < C::CP; c++) {
+                        const int buf = (sg * C::CP + c) % C::NBUF;
+                        mbar_wait_parked(g ? &acc_full_odd[buf] : &acc_full[buf], pf[buf], 200);
+                        pf[buf] ^= 1u;
+                        tc_fence_after();
+#pragma unroll
+                        for (int half = 0; half < 2; half++) {
+                            const uint32_t tcol = tmem + lane_base + buf * C::N + half * 64;
+                            uint32_t v[64];                    // 8 clusters x 8 columns
+                            tmem_ld_32x32(tcol, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                            tmem_ld_32x32(tcol + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+                            tmem_ld_wait();
+                            if (half == 1) {                   // the whole block is in registers: hand the buffer back
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; i++) {
+                                sq_acc2(qs[half * 8 + i], v[i * 8 + 0], v[i * 8 + 1]);
+                                sq_acc2(qs[half * 8 + i], v[i * 8 + 2], v[i * 8 + 3]);
+                                sq_acc2(qs[half * 8 + i], v[i * 8 + 4], v[i * 8 + 5]);
+                                sq_acc2(qs[half * 8 + i], v[i * 8 + 6], v[i * 8 + 7]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < C::GB; i++) {
+                        float lo, hi;
+                        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(qs[i]));
+                        const float l = fmaf(-0.5f * kLog2e, lo + hi, ck_s[sg * C::GB + i]);
+                        lg[sg * C::GB + i] = l;
+                        mx = fmaxf(mx, l);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < C::GB; i++) lg[sg * C::GB + i] = -INFINITY;
+                }
+            }
+            float sm = 0.f;                                    // estep2, gaussian_kernel.cu:481-503
+#pragma unroll
+            for (int j = 0; j < C::MAXSG * C::GB; j++) { lg[j] = ex2_approx(lg[j] - mx); sm += lg[j]; }
+            const float denom = fmaf(mx, kLn2, logf(sm));
+            const float scale = 1.0f / sm;
+            if (e < n) {
+                if (den_out) den_out[e] = denom;
+                else ll_acc += (double)denom;
+                float* gp = memb + e;
+#pragma unroll
+                for (int kg = 0; kg < C::MAXSG * C::GB / 8; kg++) {          // whole 8-cluster groups (rows padded to 8)
+                    if (kg * 8 < K) {
+                        float* gq = gp + (size_t)(kg * 8) * pitch;
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            *gq = lg[kg * 8 + i] * scale;                    // :498-501
+                            gq += pitch;
+                        }
+                    }
+                }
+            }
+        }
+        if (den_out == nullptr) {
+            ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 16);
+            ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 8);
+            ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 4);
+            ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 2);
+            ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 1);
+            if (lane == 0) atomicAdd(ll_out, ll_acc);
+        }
+      } else {
         const int wg = (warp - 8) >> 2, q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
@@ -702,7 +809,8 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
             ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 1);
             if (lane == 0) atomicAdd(ll_out, ll_acc);
         }
-    }
+          }
+}
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc<512>(tmem);
@@ -786,6 +894,7 @@ struct TcState {
     int e_ck_len = 0;                // Kmax rounded up to whole passes of 64
     int e_NG = 0;
     int host_threads = 8;
+    bool estep_alt = false;          // experimental alternating-warpgroup E-step epilogue (GMM_ESTEP_ALT=1)
     int gamma_split = 2;             // M-step: FP16 hi/lo pair for the responsibilities: 0 never, 1 always, 2 by cluster size
     double h_shift[GMM_MAX_DIMENSIONS] = {0}, h_scale[GMM_MAX_DIMENSIONS] = {0};
 };
@@ -834,6 +943,7 @@ int tc_create(TcState** out, const float* d_x_aos, const float* d_x_soa, int n, 
               cudaStream_t stream) {
     (void)stream;
     TcState* t = new TcState();
+    if (const char* alt = getenv("GMM_ESTEP_ALT")) t->estep_alt = atoi(alt) != 0;
     t->d_x = d_x_aos; t->d_x_soa = d_x_soa; t->d_memb = d_memb; t->memb_pitch = memb_pitch; t->n = n; t->D = D; t->Kmax = Kmax; t->num_sms = num_sms;
     *out = t;
     if (n <= 0 || !tc_mstep_supported(D, Kmax)) return GMM_OK;
@@ -1077,9 +1187,11 @@ static int launch_estep_d(TcState* t, int K, double* d_ll, cudaStream_t stream) 
     static_assert(C::SMEM_BYTES <= 232448, "shared memory budget");
     static bool attr = false;
     if (!attr) {
-        TC_CUDA_TRY(cudaFuncSetAttribute(estep_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        TC_CUDA_TRY(cudaFuncSetAttribute(estep_tc_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        TC_CUDA_TRY(cudaFuncSetAttribute(estep_tc_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr = true;
     }
+    auto kernel = t->estep_alt ? estep_tc_kernel<D, true> : estep_tc_kernel<D, false>;
     const int ntiles = (t->n + 127) / 128;
     int grid = t->num_sms;
     if (grid > ntiles) grid = ntiles;
@@ -1088,7 +1200,7 @@ static int launch_estep_d(TcState* t, int K, double* d_ll, cudaStream_t stream) 
     if (NP > 1 && !t->d_den) return fail(GMM_ERR_STATE, "tensor E-step: context was created for at most 64 clusters");
     for (int p = 0; p < NP; p++) {
         const int Kp = K - 64 * p < 64 ? K - 64 * p : 64;
-        estep_tc_kernel<D><<<grid, kEThreads, C::SMEM_BYTES, stream>>>(
+        kernel<<<grid, kEThreads, C::SMEM_BYTES, stream>>>(
             t->d_x, t->d_bimg + (size_t)p * C::MAXSG * C::B_SG, t->d_ck + 64 * p, t->d_shift_f, t->d_inv_scale_f,
             t->d_memb + (size_t)(64 * p) * t->memb_pitch, t->memb_pitch, t->n, Kp, (Kp + C::GB - 1) / C::GB, d_ll,
             NP > 1 ? t->d_den + (size_t)p * t->memb_pitch : nullptr);
