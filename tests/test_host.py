@@ -205,3 +205,23 @@ def test_cli_argument_rules(pkg, tmp_path):
     if not have_gpu():
         r = run("4", str(data), str(tmp_path / "out"))
         assert r.returncode == 255 and "No CUDA capable GPUs" in r.stdout     # main returns -1
+
+
+def test_host_finalize_is_shift_invariant(pkg):
+    """The packed statistics may be taken about any centre: the finalised N / means / covariances
+    must not depend on the shift (the engine uses the float-rounded global mean)."""
+    rng = np.random.default_rng(21)
+    N, D, K = 4000, 6, 3
+    ev = (rng.standard_normal((N, D)) * rng.uniform(0.5, 2.0, D) + rng.uniform(-30, 30, D)).astype(np.float32)
+    memb = rng.dirichlet(np.ones(K), size=N).T.astype(np.float32)
+    outs = []
+    for shift in (np.zeros(D), ev.mean(0).astype(np.float64), ev.mean(0).astype(np.float64) + 3.0):
+        cl = pkg.Clusters(K, D, 0)
+        cl.avgvar[:] = 0.01
+        pkg.host_finalize(numpy_stats(pkg, ev, memb, shift, K), shift, cl, K)
+        outs.append(cl)
+    for o in outs[1:]:
+        np.testing.assert_allclose(o.N, outs[0].N, rtol=1e-7)
+        np.testing.assert_allclose(o.means, outs[0].means, rtol=1e-6, atol=1e-5)
+        np.testing.assert_allclose(o.R, outs[0].R, rtol=2e-4, atol=2e-4)      # shift 0 cancels |mu|^2 ~ 900 against sigma^2 ~ 1
+        np.testing.assert_allclose(o.constant, outs[0].constant, rtol=1e-4)

@@ -199,3 +199,40 @@ def test_oracle_matches_reference_golden(pkg, oracle64, oracle32):
             rows = [l.rstrip("\n").split("\t") for l in open(res)]
             memb = np.array([[float(v) for v in r[1].split(",")] for r in rows])
             np.testing.assert_allclose(cl.memberships[:, :len(rows)].T, memb, atol=2e-4)
+
+
+def test_estep_permutation_equivariance_and_mstep_linearity(pkg, oracle64):
+    """Size-independent properties the GPU parity tests rely on at full size: relabelling the
+    clusters permutes the responsibilities and leaves the log-likelihood unchanged; the
+    M-step statistics are linear in the responsibilities (N_k and N_k * mean_k add up)."""
+    ev = small_problem(pkg, N=2500, D=5, K=4, seed=11)
+    N, D = ev.shape
+    K = 4
+    soa = oracle64.transpose(ev)
+    cl = random_spd_params(pkg, K, D, rng=np.random.default_rng(5))
+    cl.memberships = np.zeros((K, N), np.float32)
+    oracle64.constants(cl, K)
+    ll = oracle64.estep(soa, cl, K)
+    perm = np.array([2, 0, 3, 1])
+    cp = cl.copy()
+    for name in ("N", "pi", "constant", "avgvar"):
+        getattr(cp, name)[:] = getattr(cl, name)[perm]
+    cp.means[:] = cl.means[perm]; cp.R[:] = cl.R[perm]; cp.Rinv[:] = cl.Rinv[perm]
+    cp.memberships = np.zeros((K, N), np.float32)
+    llp = oracle64.estep(soa, cp, K)
+    assert abs(ll - llp) <= 1e-6 * abs(ll)
+    np.testing.assert_allclose(cp.memberships, cl.memberships[perm], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(cl.memberships.sum(0), 1.0, atol=1e-5)
+
+    # linearity: split the responsibilities of every cluster into two parts a + b
+    rng = np.random.default_rng(6)
+    w = rng.uniform(0.2, 0.8, size=(K, N)).astype(np.float32)
+    full, pa, pb = cl.copy(), cl.copy(), cl.copy()
+    full.memberships = cl.memberships.copy()
+    pa.memberships = (cl.memberships * w).astype(np.float32)
+    pb.memberships = (cl.memberships - pa.memberships).astype(np.float32)
+    for c in (full, pa, pb):
+        oracle64.mstep(soa, c, K)
+    np.testing.assert_allclose(pa.N + pb.N, full.N, rtol=2e-6)
+    np.testing.assert_allclose(pa.N[:, None] * pa.means + pb.N[:, None] * pb.means, full.N[:, None] * full.means,
+                               rtol=1e-4, atol=1e-3)
