@@ -5,6 +5,9 @@
 //   T2  rounding behaviour of the FP32 accumulation in TMEM (RN vs truncation).
 //   T3  MMA issue throughput for the shapes of the M-step (N=64) and E-step (N=192).
 //   T4  tcgen05.ld throughput (TMEM -> registers).
+//   T5  LBO = 0 aliasing of the two K chunks of a B operand step.
+//   T6  do tcgen05.mma accumulation and tcgen05.ld of other TMEM columns overlap?  (written at the end of round 1,
+//       not yet run: decides whether the E-step is bound by MMA + TMEM-read in series or by the epilogue warps)
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -187,6 +190,82 @@ __global__ void __launch_bounds__(256, 1) probe_ld2_kernel(int iters, int mode, 
     if (threadIdx.x < 32) tmem_dealloc<512>(tmem);
 }
 
+
+// T6: do tcgen05.mma (accumulating into TMEM) and tcgen05.ld (reading OTHER TMEM columns) overlap?
+//   what = 1: MMAs only (warp 0, one thread: `mmas` x (M=128, N=128, K=16), round-robin over 2 accumulators in columns 0..255)
+//   what = 2: loads only (warps 4..11: `loads` x tcgen05.ld.32x32b.x32 pairs of columns 256..511 + packed squares)
+//   what = 3: both at once.  cycles[0] = MMA span, cycles[1] = load span (max over the load warps' leaders).
+__global__ void __launch_bounds__(384, 1) probe_overlap_kernel(int what, int mmas, int loads, long long* cycles, float* sink) {
+    extern __shared__ __align__(1024) uint8_t smem[];            // 2 x 4 KB operand images, zero
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ long long ld_span[8];
+    for (int i = threadIdx.x * 16; i < 8192; i += blockDim.x * 16) *(uint4*)(smem + i) = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (threadIdx.x < 32) tmem_alloc<512>(&tmem_base_s);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned long long p0 = 0, p1 = 0;
+    if (warp == 0) {
+        if (lane == 0 && (what & 1)) {
+            const uint32_t idesc = make_idesc_f16(128, 128, false, false);
+            const uint64_t ad = make_smem_desc(smem_u32(smem), 2048, 128);
+            const uint64_t bd = make_smem_desc(smem_u32(smem + 4096), 2048, 128);
+            long long t0 = clock64();
+            mma_f16_ss(tmem, ad, bd, idesc, false);
+            mma_f16_ss(tmem + 128, ad, bd, idesc, false);
+#pragma unroll 1
+            for (int r = 2; r < mmas; r += 2) {
+                mma_f16_ss(tmem, ad, bd, idesc, true);
+                mma_f16_ss(tmem + 128, ad, bd, idesc, true);
+            }
+            mma_commit(&bar);
+            mbar_wait(&bar, 0);
+            cycles[0] = clock64() - t0;
+        }
+    } else if (warp >= 4 && (what & 2)) {
+        const uint32_t lane_base = ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t col0 = 256 + ((warp - 4) >> 2) * 128;       // warpgroup 0: columns 256..383, warpgroup 1: 384..511
+        long long t0 = clock64();
+#pragma unroll 1
+        for (int it = 0; it < loads; it++) {
+#pragma unroll
+            for (int c0 = 0; c0 < 128; c0 += 64) {
+                uint32_t r[32], q[32];
+                tmem_ld_32x32(tmem + lane_base + col0 + c0, r);
+                tmem_ld_32x32(tmem + lane_base + col0 + c0 + 32, q);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    unsigned long long v0 = ((unsigned long long)r[j + 1] << 32) | r[j];
+                    unsigned long long v1 = ((unsigned long long)r[j + 3] << 32) | r[j + 2];
+                    unsigned long long w0 = ((unsigned long long)q[j + 1] << 32) | q[j];
+                    unsigned long long w1 = ((unsigned long long)q[j + 3] << 32) | q[j + 2];
+                    asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(p0) : "l"(v0));
+                    asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(p1) : "l"(v1));
+                    asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(p0) : "l"(w0));
+                    asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(p1) : "l"(w1));
+                }
+            }
+        }
+        long long t1 = clock64();
+        if (lane == 0) ld_span[warp - 4] = t1 - t0;
+    }
+    if (p0 + p1 == 0x1234ull) sink[0] = 1.0f;
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0 && (what & 2)) {
+        long long m = 0;
+        for (int w = 0; w < 8; w++) m = ld_span[w] > m ? ld_span[w] : m;
+        cycles[1] = m;
+    }
+    if (threadIdx.x < 32) tmem_dealloc<512>(tmem);
+}
+
 // ---- host-side layout builders (the formulas of tc_ptx.cuh) -----------------
 static void put_h(std::vector<uint8_t>& img, size_t off, float v) {
     __half h = __float2half_rn(v);
@@ -362,6 +441,24 @@ int main() {
         long long c; CK(cudaMemcpy(&c, dcyc, 8, cudaMemcpyDeviceToHost));
         double bytes = 2000.0 * 128 * 192 * 4;
         printf("T4 tcgen05.ld 32x32b.x32 + 32 FFMA per load, 4 warps: %.1f cycles per 128x192 tile, %.1f B/cycle/SM\n", c / 2000.0, bytes / c);
+    }
+    // ---- T6: overlap of tcgen05.mma accumulation and tcgen05.ld of other columns ----
+    {
+        long long* dcyc; float* sink;
+        CK(cudaMalloc(&dcyc, 16)); CK(cudaMalloc(&sink, 4));
+        CK(cudaFuncSetAttribute(probe_overlap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192));
+        const int mmas = 8192;                    // 8192 x 64 cycles at the floor
+        const int loads = 2048;                   // per warpgroup: 2048 x 64 KB
+        for (int what = 1; what <= 3; what++) {
+            long long h[2] = {0, 0};
+            CK(cudaMemcpy(dcyc, h, 16, cudaMemcpyHostToDevice));
+            probe_overlap_kernel<<<1, 384, 8192>>>(what, mmas, loads, dcyc, sink);
+            CK(cudaDeviceSynchronize());
+            CK(cudaMemcpy(h, dcyc, 16, cudaMemcpyDeviceToHost));
+            printf("T6 %s: MMA span %lld cycles (%.1f per MMA), load span %lld cycles (%.1f B/cycle/SM)\n",
+                   what == 1 ? "MMA only  " : what == 2 ? "loads only" : "both      ", h[0], h[0] / (double)mmas, h[1],
+                   h[1] ? 2.0 * loads * 128.0 * 128 * 4 / (double)h[1] : 0.0);
+        }
     }
     printf("probe done\n");
     return 0;
