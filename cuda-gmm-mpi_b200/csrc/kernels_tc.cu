@@ -66,8 +66,20 @@ using namespace ptx;
 #endif
 constexpr int kTE = 32;          // events per sub-tile (MMA K extent per operand part)
 constexpr int kNCL = 64;         // clusters per CTA pass (MMA N)
-constexpr int kNST = 3;          // operand stages
-constexpr int kNRAW = 4;         // raw (TMA) stages
+// Pipeline depth.  GMM_MSTEP_NST / GMM_MSTEP_NRAW / GMM_MSTEP_TRIM are build-time experiment knobs (defaults = the validated
+// configuration): a fourth operand stage fits when the phi images are trimmed to their real rows and two raw stages
+// are given up (D = 24: 223.7 KB) — the builders were measured waiting on op_empty once per tile (profiles/).
+#ifndef GMM_MSTEP_NST
+#define GMM_MSTEP_NST 3
+#endif
+#ifndef GMM_MSTEP_NRAW
+#define GMM_MSTEP_NRAW 4
+#endif
+#ifndef GMM_MSTEP_TRIM
+#define GMM_MSTEP_TRIM 0
+#endif
+constexpr int kNST = GMM_MSTEP_NST;      // operand stages
+constexpr int kNRAW = GMM_MSTEP_NRAW;    // raw (TMA) stages
 constexpr int kChunkSub = GMM_CHUNKSUB;     // sub-tiles between TMEM flushes
 constexpr int kMThreads = 512;
 constexpr float kGammaScale = 1024.0f;   // responsibilities are scaled by 2^10 before the FP16 split
@@ -76,7 +88,10 @@ template <int D> struct MCfg {
     static constexpr int F = 1 + D + D * (D + 1) / 2;
     static constexpr int NCHUNK = (F + 7) / 8;            // 16-byte feature chunks actually written
     static constexpr int MT = (F + 127) / 128;            // M tiles of 128 feature rows
-    static constexpr int PHI_PART = MT * 128 * kTE * 2;   // bytes of one precision part (hi or lo)
+    // bytes of one precision part (hi or lo).  Trimmed: only the NCHUNK real 8-row groups; the last M tile's descriptor then
+    // reads past the part into whatever follows (finite FP16 data of the next part / stage / the responsibility images):
+    // garbage only in output rows >= 8 * NCHUNK, which nobody reads.
+    static constexpr int PHI_PART = GMM_MSTEP_TRIM ? NCHUNK * 8 * kTE * 2 : MT * 128 * kTE * 2;
     static constexpr int PHI_STAGE = 2 * PHI_PART;
     static constexpr int G_PART = kNCL * kTE * 2;
     static constexpr int G_STAGE = 2 * G_PART;
