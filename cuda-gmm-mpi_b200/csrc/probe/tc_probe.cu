@@ -6,8 +6,8 @@
 //   T3  MMA issue throughput for the shapes of the M-step (N=64) and E-step (N=192).
 //   T4  tcgen05.ld throughput (TMEM -> registers).
 //   T5  LBO = 0 aliasing of the two K chunks of a B operand step.
-//   T6  do tcgen05.mma accumulation and tcgen05.ld of other TMEM columns overlap?  (written at the end of round 1,
-//       not yet run: decides whether the E-step is bound by MMA + TMEM-read in series or by the epilogue warps)
+//   T6  do tcgen05.mma accumulation and tcgen05.ld of other TMEM columns overlap?  (round 1 result:
+//       they overlap completely — 64.0 cycles per MMA and 429 B/clk of loads together vs 64.0 / 443 alone)
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
