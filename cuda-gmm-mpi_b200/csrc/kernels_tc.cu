@@ -460,7 +460,7 @@ constexpr int kEThreads = 512;
 // ("block" c) only need the K chunks z_j with j >= c.  Columns are therefore grouped by block:
 // one MMA N tile = block c of 16 clusters (N = 128), and block c issues only the k-steps it needs —
 // 5 + 4 + 2 = 11 instead of 15 at D = 24 (-27 % tensor work and TMEM accumulator traffic).
-template <int D> struct ECfg {
+template <int D, int NWG = 2> struct ECfg {
     static_assert(D % 8 == 0, "tensor E-step: D must be a multiple of 8");
     static constexpr int CP = D / 8;                          // 8-wide chunks of z / blocks of output columns
     static constexpr int NLO = (CP + 1 + 1) / 2 * 2;          // chunks of the [zh | ones (| pad)] x [Wl | v] part
@@ -470,33 +470,38 @@ template <int D> struct ECfg {
     static constexpr int N = GB * 8;                          // MMA N = one block of a supergroup (128 columns)
     static constexpr int MAXSG = 64 / GB;                     // up to 64 clusters resident
     static constexpr int NBUF = 512 / N;                      // TMEM accumulator buffers (4)
-    static constexpr int CW = GB / 2;                         // clusters per epilogue warpgroup per supergroup
-    static constexpr int LPT = MAXSG * CW;                    // logits held per epilogue thread (= 32)
+    static constexpr int CW = GB / NWG;                       // clusters per epilogue warpgroup per supergroup
+    static constexpr int LPT = MAXSG * CW;                    // logits held per epilogue thread (32, or 16 with 4 warpgroups)
     static constexpr int A_STAGE = NCHKA * 128 * 16;
     static constexpr int B_BLOCK = NCHKB * N * 16;            // one block of one supergroup
     static constexpr int B_SG = CP * B_BLOCK;
     static constexpr int OFF_B = 0;
     static constexpr int OFF_A = OFF_B + MAXSG * B_SG;
     static constexpr int OFF_CK = OFF_A + 2 * A_STAGE;        // float[64] constant + ln(pi)
-    static constexpr int OFF_EX = OFF_CK + 256;               // exchange: [2 parity][2 wg][128] x (max, sum)
-    static constexpr int OFF_BAR = OFF_EX + 2 * 2 * 128 * 8;
+    static constexpr int OFF_EX = OFF_CK + 256;               // exchange: [2 parity][NWG][128] x (max, sum)
+    static constexpr int OFF_BAR = OFF_EX + 2 * NWG * 128 * 8;
     static constexpr int SMEM_BYTES = OFF_BAR + 512;
-    static_assert(LPT == 32, "logits per thread");
+    static constexpr int THREADS = 256 + 128 * NWG;           // warpgroup 0, converters, NWG epilogue warpgroups
+    static_assert(NWG == 2 || NWG == 4, "epilogue warpgroups");
 };
 
 // ALT = false: both epilogue warpgroups work on every tile (each takes 8 of the 16 clusters of a supergroup and they
 // exchange (max, sum) through shared memory).  ALT = true (experimental, GMM_ESTEP_ALT=1): the warpgroups take alternate
 // tiles and each handles all 16 clusters — no exchange, and the log-sum-exp / store phase of one tile overlaps the
 // accumulator reads of the next, so the MMA issuer is not held up by full TMEM buffers during that phase.
-template <int D, bool ALT>
-__global__ void __launch_bounds__(kEThreads, 1)
+// NWG = 4 (experimental, GMM_ESTEP_WG4=1): four epilogue warpgroups, each with 4 of the 16 clusters of a supergroup (one
+// tcgen05.ld.x32 per block and warp, 16 logits per thread, 96 registers) — four instead of two epilogue warps per sub-core
+// to hide the load / mbarrier / MUFU latencies the two-warp version exposes (tc_probe T6: the hardware floor is the MMA time).
+template <int D, bool ALT, int NWG = 2>
+__global__ void __launch_bounds__(256 + 128 * NWG, 1)
 estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_img, const float* __restrict__ ck,
                 const float* __restrict__ shift_f, const float* __restrict__ inv_scale_f, float* __restrict__ memb,
                 size_t pitch, int n, int K, int NSG, double* __restrict__ ll_out, float* __restrict__ den_out) {
     // K / NSG / b_img / ck / memb describe ONE pass of at most 64 clusters.  With more than 64 clusters the host
     // launches one pass per 64 (den_out != nullptr): each pass normalises within itself and records its
     // log-denominator per event; estep_tc_combine_kernel then rescales the passes against each other.
-    using C = ECfg<D>;
+    using C = ECfg<D, NWG>;
+    static_assert(!ALT || NWG == 2, "alternate-tile epilogue is written for two warpgroups");
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
     uint64_t* a_full = bars;            // [2]  4 converter warps
@@ -519,7 +524,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; s++) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < C::NBUF; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], ALT ? 4 : 8); }
+        for (int s = 0; s < C::NBUF; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], ALT ? 4 : 4 * NWG); }
         mbar_init(b_full, 1);
         if (ALT) for (int s = 0; s < C::NBUF; s++) mbar_init(&acc_full_odd[s], 1);
         fence_mbar_init();
@@ -540,7 +545,9 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
 
     // register re-partition inside the CTA's launch allocation (512 x 128): WG0 40, converters 72, epilogue 2 x 200
     if (warp < 4) {
-      if constexpr (ALT) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+      // register pools: NWG = 2 launches 512 x 128, NWG = 4 launches 768 x 80 (= 61440): 128 x (24 + 64) + 512 x 96 = 60416
+      if constexpr (NWG == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+      else if constexpr (ALT) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
       else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
       if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -586,7 +593,8 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
         }
       }
     } else if (warp < 8) {
-        if constexpr (ALT) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        if constexpr (NWG == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        else if constexpr (ALT) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
         // ===================== converters =====================
         const int row = threadIdx.x - 128;
@@ -633,7 +641,8 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
             if (lane == 0) mbar_arrive(&a_full[st]);
         }
     } else {
-        if constexpr (ALT) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");   // 128 x (32 + 64 + 2 x 208) = 64K registers
+        if constexpr (NWG == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+        else if constexpr (ALT) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");   // 128 x (32 + 64 + 2 x 208) = 64K registers
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
         // ===================== epilogue =====================
       if constexpr (ALT) {
@@ -756,19 +765,27 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                         pf[buf] ^= 1u;
                         tc_fence_after();
                         const uint32_t tcol = tmem + lane_base + buf * C::N + wg * (C::CW * 8);
-                        uint32_t v[C::CW * 8];                 // 8 clusters x 8 columns
+                        uint32_t v[C::CW * 8];                 // CW clusters x 8 columns
                         tmem_ld_32x32(tcol, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-                        tmem_ld_32x32(tcol + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+                        if constexpr (C::CW * 8 > 32) tmem_ld_32x32(tcol + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[C::CW * 8 - 32]));
                         tmem_ld_wait();
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&acc_empty[buf]);   // the block is in registers: hand the buffer back
 #pragma unroll
                         for (int i = 0; i < C::CW; i++) {
-                            sq_acc2(qa[i], v[i * 8 + 0], v[i * 8 + 1]);
-                            sq_acc2(qb[i], v[i * 8 + 2], v[i * 8 + 3]);
-                            sq_acc2(qa[i], v[i * 8 + 4], v[i * 8 + 5]);
-                            sq_acc2(qb[i], v[i * 8 + 6], v[i * 8 + 7]);
+                            if constexpr (NWG == 2) {
+                                sq_acc2(qa[i], v[i * 8 + 0], v[i * 8 + 1]);
+                                sq_acc2(qb[i], v[i * 8 + 2], v[i * 8 + 3]);
+                                sq_acc2(qa[i], v[i * 8 + 4], v[i * 8 + 5]);
+                                sq_acc2(qb[i], v[i * 8 + 6], v[i * 8 + 7]);
+                            } else {                           // 96-register budget: one accumulator pair per cluster
+                                sq_acc2(qa[i], v[i * 8 + 0], v[i * 8 + 1]);
+                                sq_acc2(qa[i], v[i * 8 + 2], v[i * 8 + 3]);
+                                sq_acc2(qa[i], v[i * 8 + 4], v[i * 8 + 5]);
+                                sq_acc2(qa[i], v[i * 8 + 6], v[i * 8 + 7]);
+                                asm volatile("" : "+l"(qa[i]));   // keep this block's squares ahead of the next block's load (register budget)
+                            }
                         }
                     }
 #pragma unroll
@@ -786,13 +803,25 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
             float sm = 0.f;
 #pragma unroll
             for (int j = 0; j < C::LPT; j++) { lg[j] = ex2_approx(lg[j] - mx); sm += lg[j]; }
-            float2* exb = ex + (it & 1) * 256;
+            float2* exb = ex + (it & 1) * (NWG * 128);
             exb[wg * 128 + row] = make_float2(mx, sm);
-            named_bar_sync(1, 256);
-            const float2 o = exb[(wg ^ 1) * 128 + row];
-            const float M = fmaxf(mx, o.x);
-            const float own = ex2_approx(mx - M);
-            const float S = sm * own + o.y * ex2_approx(o.x - M);
+            named_bar_sync(1, NWG * 128);
+            float M, own, S;
+            if constexpr (NWG == 2) {
+                const float2 o = exb[(wg ^ 1) * 128 + row];
+                M = fmaxf(mx, o.x);
+                own = ex2_approx(mx - M);
+                S = sm * own + o.y * ex2_approx(o.x - M);
+            } else {
+                float2 o[NWG];
+                M = mx;
+#pragma unroll
+                for (int w = 0; w < NWG; w++) { o[w] = exb[w * 128 + row]; M = fmaxf(M, o[w].x); }
+                own = ex2_approx(mx - M);
+                S = 0.f;
+#pragma unroll
+                for (int w = 0; w < NWG; w++) S += o[w].y * ex2_approx(o[w].x - M);
+            }
             const float denom = fmaf(M, kLn2, logf(S));              // :490-494, back in natural units
             const float scale = own / S;                             // exp(l - denom) = 2^(l2 - mx) * 2^(mx - M) / S
             if (e < n) {
@@ -910,6 +939,7 @@ struct TcState {
     int e_NG = 0;
     int host_threads = 8;
     bool estep_alt = false;          // experimental alternating-warpgroup E-step epilogue (GMM_ESTEP_ALT=1)
+    bool estep_wg4 = false;          // experimental four-warpgroup E-step epilogue (GMM_ESTEP_WG4=1)
     int gamma_split = 2;             // M-step: FP16 hi/lo pair for the responsibilities: 0 never, 1 always, 2 by cluster size
     double h_shift[GMM_MAX_DIMENSIONS] = {0}, h_scale[GMM_MAX_DIMENSIONS] = {0};
 };
@@ -959,6 +989,7 @@ int tc_create(TcState** out, const float* d_x_aos, const float* d_x_soa, int n, 
     (void)stream;
     TcState* t = new TcState();
     if (const char* alt = getenv("GMM_ESTEP_ALT")) t->estep_alt = atoi(alt) != 0;
+    if (const char* wg4 = getenv("GMM_ESTEP_WG4")) t->estep_wg4 = atoi(wg4) != 0;
     t->d_x = d_x_aos; t->d_x_soa = d_x_soa; t->d_memb = d_memb; t->memb_pitch = memb_pitch; t->n = n; t->D = D; t->Kmax = Kmax; t->num_sms = num_sms;
     *out = t;
     if (n <= 0 || !tc_mstep_supported(D, Kmax)) return GMM_OK;
@@ -1207,6 +1238,19 @@ static int launch_estep_d(TcState* t, int K, double* d_ll, cudaStream_t stream) 
         attr = true;
     }
     auto kernel = t->estep_alt ? estep_tc_kernel<D, true> : estep_tc_kernel<D, false>;
+    int threads = kEThreads, smem_bytes = C::SMEM_BYTES;
+    if (t->estep_wg4) {
+        using C4 = ECfg<D, 4>;
+        static_assert(C4::SMEM_BYTES <= 232448, "shared memory budget");
+        static bool attr4 = false;
+        if (!attr4) {
+            TC_CUDA_TRY(cudaFuncSetAttribute(estep_tc_kernel<D, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, C4::SMEM_BYTES));
+            attr4 = true;
+        }
+        kernel = estep_tc_kernel<D, false, 4>;
+        threads = C4::THREADS;
+        smem_bytes = C4::SMEM_BYTES;
+    }
     const int ntiles = (t->n + 127) / 128;
     int grid = t->num_sms;
     if (grid > ntiles) grid = ntiles;
@@ -1215,7 +1259,7 @@ static int launch_estep_d(TcState* t, int K, double* d_ll, cudaStream_t stream) 
     if (NP > 1 && !t->d_den) return fail(GMM_ERR_STATE, "tensor E-step: context was created for at most 64 clusters");
     for (int p = 0; p < NP; p++) {
         const int Kp = K - 64 * p < 64 ? K - 64 * p : 64;
-        kernel<<<grid, kEThreads, C::SMEM_BYTES, stream>>>(
+        kernel<<<grid, threads, smem_bytes, stream>>>(
             t->d_x, t->d_bimg + (size_t)p * C::MAXSG * C::B_SG, t->d_ck + 64 * p, t->d_shift_f, t->d_inv_scale_f,
             t->d_memb + (size_t)(64 * p) * t->memb_pitch, t->memb_pitch, t->n, Kp, (Kp + C::GB - 1) / C::GB, d_ll,
             NP > 1 ? t->d_den + (size_t)p * t->memb_pitch : nullptr);
