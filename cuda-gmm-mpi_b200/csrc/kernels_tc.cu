@@ -456,6 +456,18 @@ mstep_tc_finalize_kernel(const double* __restrict__ scratch, int ncta_x, int MT,
 // ===========================================================================
 constexpr int kEThreads = 512;
 
+// GMM_ESTEP_PROF=1 (build-time, diagnostic variant only): the epilogue of CTA 0 / warp 8 accumulates clock64() spans of its
+// phases and prints them at the end of the kernel — where do the cycles of a tile go (waiting for accumulators, tcgen05.ld,
+// squares, logits + log-sum-exp + exchange, stores)?  Off by default: no code is generated.
+#ifndef GMM_ESTEP_PROF
+#define GMM_ESTEP_PROF 0
+#endif
+#if GMM_ESTEP_PROF
+#define EPROF(stmt) stmt
+#else
+#define EPROF(stmt)
+#endif
+
 // Block structure.  W is upper triangular, so the 8 output columns d in [8c, 8c+8) of a cluster
 // ("block" c) only need the K chunks z_j with j >= c.  Columns are therefore grouped by block:
 // one MMA N tile = block c of 16 clusters (N = 128), and block c issues only the k-steps it needs —
@@ -744,6 +756,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         double ll_acc = 0.0;
+        EPROF(long long pr_wait = 0; long long pr_ld = 0; long long pr_sq = 0; long long pr_lse = 0; long long pr_st = 0; long long pr_t0 = clock64();)
         uint32_t pf[C::NBUF];                                  // wait parity of acc_full[b]; b is static after unrolling
 #pragma unroll
         for (int b = 0; b < C::NBUF; b++) pf[b] = 0u;
@@ -761,14 +774,17 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
 #pragma unroll
                     for (int c = 0; c < C::CP; c++) {
                         const int buf = (sg * C::CP + c) % C::NBUF;   // compile-time: the sequence restarts with every tile
+                        EPROF(const long long p0 = clock64();)
                         mbar_wait_parked(&acc_full[buf], pf[buf], 200);
                         pf[buf] ^= 1u;
                         tc_fence_after();
+                        EPROF(const long long p1 = clock64(); pr_wait += p1 - p0;)
                         const uint32_t tcol = tmem + lane_base + buf * C::N + wg * (C::CW * 8);
                         uint32_t v[C::CW * 8];                 // CW clusters x 8 columns
                         tmem_ld_32x32(tcol, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
                         if constexpr (C::CW * 8 > 32) tmem_ld_32x32(tcol + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[C::CW * 8 - 32]));
                         tmem_ld_wait();
+                        EPROF(const long long p2 = clock64(); pr_ld += p2 - p1;)
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&acc_empty[buf]);   // the block is in registers: hand the buffer back
@@ -787,6 +803,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                                 asm volatile("" : "+l"(qa[i]));   // keep this block's squares ahead of the next block's load (register budget)
                             }
                         }
+                        EPROF(asm volatile("" : "+l"(qa[0])); pr_sq += clock64() - p2;)
                     }
 #pragma unroll
                     for (int i = 0; i < C::CW; i++) {
@@ -800,6 +817,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                 }
             }
             // log-sum-exp over the clusters (estep2, gaussian_kernel.cu:481-503): local part, then the two warpgroups combine
+            EPROF(const long long p3 = clock64();)
             float sm = 0.f;
 #pragma unroll
             for (int j = 0; j < C::LPT; j++) { lg[j] = ex2_approx(lg[j] - mx); sm += lg[j]; }
@@ -824,6 +842,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
             }
             const float denom = fmaf(M, kLn2, logf(S));              // :490-494, back in natural units
             const float scale = own / S;                             // exp(l - denom) = 2^(l2 - mx) * 2^(mx - M) / S
+            EPROF(const long long p4 = clock64(); pr_lse += p4 - p3;)
             if (e < n) {
                 if (wg == 0) {
                     if (den_out) den_out[e] = denom;
@@ -844,7 +863,12 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                     }
                 }
             }
+            EPROF(pr_st += clock64() - p4;)
         }
+        EPROF(if (blockIdx.x == 0 && warp == 8 && lane == 0)
+                  printf("estep epilogue profile (CTA 0, warp 8): %d tiles, cycles per tile: total %.0f = wait acc_full %.0f + tcgen05.ld %.0f + squares %.0f + "
+                         "lse/exchange %.0f + stores %.0f + rest\n", my_tiles, (double)(clock64() - pr_t0) / my_tiles, (double)pr_wait / my_tiles,
+                         (double)pr_ld / my_tiles, (double)pr_sq / my_tiles, (double)pr_lse / my_tiles, (double)pr_st / my_tiles);)
         if (wg == 0 && den_out == nullptr) {
             ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 16);
             ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 8);
