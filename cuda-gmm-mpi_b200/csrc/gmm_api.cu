@@ -75,6 +75,18 @@ struct PhaseTimer {          // replaces cudaTimer_t / profile_t (gaussian.cu:33
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
     double total_ms = 0;
 };
+// Timing events are recycled: cudaEventCreate / Destroy cost microseconds each and sat inside the EM loop.
+struct EventPool {
+    std::vector<cudaEvent_t> free_list;
+    cudaEvent_t get() {
+        if (!free_list.empty()) { cudaEvent_t e = free_list.back(); free_list.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void put(cudaEvent_t e) { if (e) free_list.push_back(e); }
+    void destroy() { for (cudaEvent_t e : free_list) cudaEventDestroy(e); free_list.clear(); }
+};
 
 }  // namespace gmm
 
@@ -108,16 +120,20 @@ struct gmm_ctx {
     clusters_t host{};
     int cur_K = 0;
     bool memb_valid = false;     // d_memb holds the responsibilities of the current parameters
+    int stats_clean_K = 0;       // d_stats[0 .. K*F) is known to be zero for this K (0 = not known)
     // communication
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
     // options
     int path = GMM_PATH_AUTO;
+    int estep_path = -1, mstep_path = -1;   // per-step override of `path` (options "estep_path" / "mstep_path"; -1 = follow `path`)
     int verbose = 0;
     int host_threads = 1;
     bool host_threads_fixed = false; // set by GMM_HOST_THREADS / gmm_set_option: not re-derived from the rank count
     // profile
     PhaseTimer t_estep, t_mstep, t_reduce, t_fused;
+    EventPool events;
+    bool profile_phases = true;  // per-phase CUDA-event timers inside the EM loop (option "profile")
     double host_const_ms = 0, memcpy_ms = 0;
     long long iterations = 0;
     TcState* tc = nullptr;       // tensor-core path state (kernels_tc.cuh)
@@ -127,22 +143,25 @@ struct gmm_ctx {
 namespace gmm {
 
 static void timer_begin(gmm_ctx* c, PhaseTimer& t) {
-    cudaEvent_t a, b;
-    cudaEventCreate(&a); cudaEventCreate(&b);
+    if (!c->profile_phases) return;
+    cudaEvent_t a = c->events.get(), b = c->events.get();
     cudaEventRecord(a, c->stream);
     t.pending.push_back({a, b});
 }
-static void timer_end(gmm_ctx* c, PhaseTimer& t) { cudaEventRecord(t.pending.back().second, c->stream); }
-static void timer_collect(PhaseTimer& t) {          // call after a stream sync
+static void timer_end(gmm_ctx* c, PhaseTimer& t) {
+    if (!c->profile_phases || t.pending.empty()) return;
+    cudaEventRecord(t.pending.back().second, c->stream);
+}
+static void timer_collect(gmm_ctx* c, PhaseTimer& t) {          // call after a stream sync
     for (auto& p : t.pending) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) t.total_ms += ms;
-        cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+        c->events.put(p.first); c->events.put(p.second);
     }
     t.pending.clear();
 }
 static void collect_all(gmm_ctx* c) {
-    timer_collect(c->t_estep); timer_collect(c->t_mstep); timer_collect(c->t_reduce); timer_collect(c->t_fused);
+    timer_collect(c, c->t_estep); timer_collect(c, c->t_mstep); timer_collect(c, c->t_reduce); timer_collect(c, c->t_fused);
 }
 
 static void bind_host(gmm_ctx* c) {
@@ -173,11 +192,13 @@ static int default_host_threads(int ranks_on_box) {
     return t;
 }
 
-static bool use_tensor_estep(const gmm_ctx* c, int K) { return c->path != GMM_PATH_SIMT && c->n > 0 && tc_estep_supported(c->D, K); }
-static bool use_tensor_mstep(const gmm_ctx* c, int K) { return c->path != GMM_PATH_SIMT && c->n > 0 && tc_mstep_supported(c->D, K); }
+static int estep_path_of(const gmm_ctx* c) { return c->estep_path >= 0 ? c->estep_path : c->path; }
+static int mstep_path_of(const gmm_ctx* c) { return c->mstep_path >= 0 ? c->mstep_path : c->path; }
+static bool use_tensor_estep(const gmm_ctx* c, int K) { return estep_path_of(c) != GMM_PATH_SIMT && c->n > 0 && tc_estep_supported(c->D, K); }
+static bool use_tensor_mstep(const gmm_ctx* c, int K) { return mstep_path_of(c) != GMM_PATH_SIMT && c->n > 0 && tc_mstep_supported(c->D, K); }
 // GMM_PATH_TENSOR never degrades silently: the M-step (the covariance contraction) must be covered.
 static int check_path(const gmm_ctx* c, int K) {
-    if (c->path == GMM_PATH_TENSOR && !tc_mstep_supported(c->D, K))
+    if (mstep_path_of(c) == GMM_PATH_TENSOR && !tc_mstep_supported(c->D, K))
         return fail(GMM_ERR_ARG, "GMM_PATH_TENSOR requested but the tcgen05 kernels do not cover this (D, K)");
     return GMM_OK;
 }
@@ -215,7 +236,7 @@ static int upload_params(gmm_ctx* c, int K, bool with_constants = false, bool wi
             rc = tc_params_commit(c->tc, K, bad, c->stream);
         }
         if (rc == GMM_OK) c->estep_tensor_ready = true;
-        else if (rc != GMM_ERR_STATE || c->path == GMM_PATH_TENSOR) return rc;
+        else if (rc != GMM_ERR_STATE || estep_path_of(c) == GMM_PATH_TENSOR) return rc;
         // GMM_ERR_STATE under GMM_PATH_AUTO: a cluster whose inverse covariance is not positive definite
         // (or does not fit FP16) — this parameter set is evaluated by the FP32 SIMT kernel instead.
     }
@@ -258,10 +279,11 @@ static int launch_mstep_simt_t(gmm_ctx* c, int K) {
     constexpr int FP = 16 * JMAX, KT = 16 * CPT, GS = KT + 2;
     const size_t smem = sizeof(double) * (size_t)(kMstepTE * FP + kMstepTE * GS + kMstepTE * GMM_MAX_DIMENSIONS) +
                         sizeof(short) * 2 * FP;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the attribute is per device (context): one flag per device, not per process (a thread per GPU in the CLI)
+    static bool attr_set[64] = {false};
+    if (c->device >= 64 || !attr_set[c->device]) {
         CUDA_TRY(cudaFuncSetAttribute(mstep_simt_kernel<JMAX, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        if (c->device < 64) attr_set[c->device] = true;
     }
     int gx = c->num_sms;
     int per = (c->n + gx - 1) / gx;
@@ -298,6 +320,7 @@ static int launch_mstep_simt(gmm_ctx* c, int K) {
 
 static int zero_stats(gmm_ctx* c, int K) {
     CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(double) * ((size_t)K * c->F + 1), c->stream));
+    c->stats_clean_K = K;
     return GMM_OK;
 }
 
@@ -314,6 +337,10 @@ static int run_estep(gmm_ctx* c, int K) {
 
 // M-step accumulation of the local statistics into stats[0 .. K*F).
 static int run_mstep_accumulate(gmm_ctx* c, int K) {
+    // Both M-step kernels ADD into stats[0 .. K*F): whatever an earlier call left there (column moments, seed rows,
+    // the reduced statistics of a finished gmm_em / gmm_mstep) has to go; the log-likelihood slot [K*F] stays.
+    if (c->stats_clean_K != K) CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(double) * (size_t)K * c->F, c->stream));
+    c->stats_clean_K = 0;
     timer_begin(c, c->t_mstep);
     float min_nk = INFINITY;                       // cluster sizes of the parameters the responsibilities came from
     for (int k = 0; k < K; k++) min_nk = std::fmin(min_nk, c->host.N[k]);
@@ -354,6 +381,7 @@ static int finalize_and_upload(gmm_ctx* c, int K) {
 static int ensure_moments(gmm_ctx* c) {
     if (c->have_shift) return GMM_OK;
     const int D = c->D;
+    c->stats_clean_K = 0;
     CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(double) * 2 * D, c->stream));
     if (c->n > 0) {
         dim3 grid(std::min(4 * c->num_sms, (c->n + 255) / 256), D);
@@ -443,6 +471,7 @@ int gmm_create(gmm_ctx** out, int device, int n_local, int D, int Kmax, const fl
     CREATE_TRY(cudaMalloc(&c->d_epack, sizeof(float) * (size_t)Kmax * epack_stride(D)));
     CREATE_TRY(cudaMallocHost(&c->h_epack, sizeof(float) * (size_t)Kmax * epack_stride(D)));
     CREATE_TRY(cudaMalloc(&c->d_stats, sizeof(double) * ((size_t)Kmax * c->F + 1)));
+    CREATE_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(double) * ((size_t)Kmax * c->F + 1), c->stream));
     CREATE_TRY(cudaMallocHost(&c->h_stats, sizeof(double) * ((size_t)Kmax * c->F + 1)));
     CREATE_TRY(cudaMalloc(&c->d_shift, sizeof(double) * GMM_MAX_DIMENSIONS));
     CREATE_TRY(cudaMemsetAsync(c->d_shift, 0, sizeof(double) * GMM_MAX_DIMENSIONS, c->stream));
@@ -477,6 +506,10 @@ int gmm_upload_events(gmm_ctx* c, const float* events_aos) {
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->have_shift = false;
     c->memb_valid = false;
+    // the resident E-step operand was built in the coordinates (shift / scale) of the previous data set:
+    // the caller has to set parameters again (gmm_seed / gmm_set_clusters) before the next E-step
+    c->estep_tensor_ready = false;
+    c->cur_K = 0;
     return GMM_OK;
 }
 
@@ -492,6 +525,7 @@ void gmm_destroy(gmm_ctx* c) {
     if (c->h_epack) cudaFreeHost(c->h_epack);
     if (c->h_stats) cudaFreeHost(c->h_stats);
     if (c->ev_stats) cudaEventDestroy(c->ev_stats);
+    c->events.destroy();
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -544,7 +578,12 @@ int gmm_set_option(gmm_ctx* c, const char* key, double value) {
         tc_set_host_threads(c->tc, c->host_threads);
     }
     else if (k == "mstep_gamma_split") { tc_set_gamma_split(c->tc, (int)value); }
-    else if (k == "write_memberships") { /* accepted; every E-step materialises memberships in this build */ }
+    else if (k == "estep_path" || k == "mstep_path") {
+        const int p = (int)value;
+        if (p < -1 || p > GMM_PATH_TENSOR) return fail(GMM_ERR_ARG, "gmm_set_option: bad path");
+        (k == "estep_path" ? c->estep_path : c->mstep_path) = p;
+    }
+    else if (k == "profile") c->profile_phases = value != 0;
     else return fail(GMM_ERR_ARG, "gmm_set_option: unknown key '" + k + "'");
     return GMM_OK;
 }
@@ -570,6 +609,7 @@ int gmm_seed(gmm_ctx* c, int K, clusters_t* host_out) {
         }
     }
     if (c->nranks > 1) {
+        c->stats_clean_K = 0;
         CUDA_TRY(cudaMemcpyAsync(c->d_stats, rows.data(), sizeof(double) * len, cudaMemcpyHostToDevice, c->stream));
         ncclResult_t r = nccl().AllReduce(c->d_stats, c->d_stats, len, ncclDouble, ncclSum, c->comm, c->stream);
         if (r != ncclSuccess) return fail(GMM_ERR_NCCL, std::string("ncclAllReduce: ") + nccl().GetErrorString(r));
@@ -637,8 +677,7 @@ int gmm_mstep(gmm_ctx* c, int K) {
     CUDA_TRY(cudaSetDevice(c->device));
     if (int rc = ensure_moments(c)) return rc;
     const double ll_keep = c->h_stats[(size_t)K * c->F];
-    CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(double) * (size_t)K * c->F, c->stream));
-    if (int rc = run_mstep_accumulate(c, K)) return rc;
+    if (int rc = run_mstep_accumulate(c, K)) return rc;         // zeroes stats[0 .. K*F) first
     if (int rc = reduce_stats_to_host(c, K)) return rc;
     c->h_stats[(size_t)K * c->F] = ll_keep;
     // gmm_mstep stops before constants_kernel: N, means, R only (gaussian.cu:538-687)

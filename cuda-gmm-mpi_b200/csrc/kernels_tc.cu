@@ -78,6 +78,19 @@ constexpr int kNCL = 64;         // clusters per CTA pass (MMA N)
 #ifndef GMM_MSTEP_TRIM
 #define GMM_MSTEP_TRIM 0
 #endif
+// Operand split of the M-step (build-time knobs, defaults = the shipped configuration):
+//   GMM_MSTEP_RN = 1  hi = round-to-nearest FP16 of the value, lo = FP16(value - hi): the dropped lo*lo product is then
+//                     zero-mean.  With the truncating split (0: hi = leading 11 bits) hi <= |value| always, lo*lo has one
+//                     sign and the three kept products carry a systematic relative bias of ~1e-7 that is different for
+//                     the count row (phi = 1: none), the first and the second moments — the raw-moment cancellation
+//                     (|mu - shift|^2 / sigma^2 ~ 100) turns it into ~1e-5 on covariance entries (scripts/emu_mstep.py).
+//   GMM_MSTEP_P4 = 1  also issue the fourth product (phi_lo, g_lo) — diagnostic only.
+#ifndef GMM_MSTEP_RN
+#define GMM_MSTEP_RN 1
+#endif
+#ifndef GMM_MSTEP_P4
+#define GMM_MSTEP_P4 0
+#endif
 constexpr int kNST = GMM_MSTEP_NST;      // operand stages
 constexpr int kNRAW = GMM_MSTEP_NRAW;    // raw (TMA) stages
 constexpr int kChunkSub = GMM_CHUNKSUB;     // sub-tiles between TMEM flushes
@@ -119,6 +132,21 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 
+// FP16 hi/lo split of a pair of values, packed as half2 bits (low half = first value).
+__device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+#if GMM_MSTEP_RN
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 f = __half22float2(h);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = pack_half2(v0 - f.x, v1 - f.y);                                   // exact remainders, rounded once
+#else
+    const float h0 = __uint_as_float(__float_as_uint(v0) & 0xFFFFE000u);   // top 11 significant bits: exact in FP16
+    const float h1 = __uint_as_float(__float_as_uint(v1) & 0xFFFFE000u);
+    hi = pack_half2(h0, h1);
+    lo = pack_half2(v0 - h0, v1 - h1);
+#endif
+}
+
 // value of feature f for centred/scaled event z (f is a compile-time constant after unrolling)
 template <int D>
 __device__ __forceinline__ float feature_value(const float (&z)[D], int f) {
@@ -143,16 +171,11 @@ __device__ __forceinline__ void build_phi_chunks(const float (&z)[D], uint8_t* h
     const int eoff = (e >> 3) * 128 + (e & 7) * 16;
 #pragma unroll
     for (int c = P; c < NCHUNK; c += 4) {
-        float hi[8], lo[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const float v = feature_value<D>(z, c * 8 + u);
-            hi[u] = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);     // top 11 significant bits: exact in FP16
-            lo[u] = v - hi[u];                                             // exact remainder
-        }
         uint4 h, l;
-        h.x = pack_half2(hi[0], hi[1]); h.y = pack_half2(hi[2], hi[3]); h.z = pack_half2(hi[4], hi[5]); h.w = pack_half2(hi[6], hi[7]);
-        l.x = pack_half2(lo[0], lo[1]); l.y = pack_half2(lo[2], lo[3]); l.z = pack_half2(lo[4], lo[5]); l.w = pack_half2(lo[6], lo[7]);
+        split_pair(feature_value<D>(z, c * 8 + 0), feature_value<D>(z, c * 8 + 1), h.x, l.x);
+        split_pair(feature_value<D>(z, c * 8 + 2), feature_value<D>(z, c * 8 + 3), h.y, l.y);
+        split_pair(feature_value<D>(z, c * 8 + 4), feature_value<D>(z, c * 8 + 5), h.z, l.z);
+        split_pair(feature_value<D>(z, c * 8 + 6), feature_value<D>(z, c * 8 + 7), h.w, l.w);
         *reinterpret_cast<uint4*>(hi_base + c * 512 + eoff) = h;
         *reinterpret_cast<uint4*>(lo_base + c * 512 + eoff) = l;
     }
@@ -232,9 +255,9 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 const uint32_t gam = smem_u32(smem + C::OFF_G + os * C::G_STAGE);
                 const uint32_t dcol = tmem + ab * (C::MT * kNCL);
 #pragma unroll
-                for (int seg = 0; seg < (GS ? 3 : 2); seg++) {   // (phi_hi, g_hi), (phi_lo, g_hi), (phi_hi, g_lo)
-                    const uint32_t pa = phi + (seg == 1 ? C::PHI_PART : 0);
-                    const uint32_t pb = gam + (seg == 2 ? C::G_PART : 0);
+                for (int seg = 0; seg < (GS ? 3 + GMM_MSTEP_P4 : 2); seg++) {   // (phi_hi, g_hi), (phi_lo, g_hi), (phi_hi, g_lo) [, (phi_lo, g_lo)]
+                    const uint32_t pa = phi + ((seg & 1) ? C::PHI_PART : 0);
+                    const uint32_t pb = gam + (seg >= 2 ? C::G_PART : 0);
 #pragma unroll
                     for (int ks = 0; ks < kTE / 16; ks++) {
                         const uint64_t bdesc = make_smem_desc(pb + ks * 256, /*LBO*/ 128, /*SBO*/ 512);
@@ -287,15 +310,12 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 float g[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
                 gdep += a.x + b.x;
                 if (GS) {
-                    float hi[8], lo[8];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const float v = g[u] * kGammaScale;
-                        hi[u] = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-                        lo[u] = v - hi[u];
-                    }
-                    gh[it2] = make_uint4(pack_half2(hi[0], hi[1]), pack_half2(hi[2], hi[3]), pack_half2(hi[4], hi[5]), pack_half2(hi[6], hi[7]));
-                    gl[it2] = make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]), pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7]));
+                    for (int u = 0; u < 8; u++) g[u] *= kGammaScale;
+                    split_pair(g[0], g[1], gh[it2].x, gl[it2].x);
+                    split_pair(g[2], g[3], gh[it2].y, gl[it2].y);
+                    split_pair(g[4], g[5], gh[it2].z, gl[it2].z);
+                    split_pair(g[6], g[7], gh[it2].w, gl[it2].w);
                 } else {
 #pragma unroll
                     for (int u = 0; u < 8; u++) g[u] *= kGammaScale;
@@ -965,6 +985,8 @@ struct TcState {
     bool estep_alt = false;          // experimental alternating-warpgroup E-step epilogue (GMM_ESTEP_ALT=1)
     bool estep_wg4 = false;          // experimental four-warpgroup E-step epilogue (GMM_ESTEP_WG4=1)
     int gamma_split = 2;             // M-step: FP16 hi/lo pair for the responsibilities: 0 never, 1 always, 2 by cluster size
+    // cudaFuncAttributeMaxDynamicSharedMemorySize is per device: the "already set" flags live with the (per-device) state
+    bool attr_estep = false, attr_estep4 = false, attr_mstep = false;
     double h_shift[GMM_MAX_DIMENSIONS] = {0}, h_scale[GMM_MAX_DIMENSIONS] = {0};
 };
 
@@ -1255,21 +1277,19 @@ template <int D>
 static int launch_estep_d(TcState* t, int K, double* d_ll, cudaStream_t stream) {
     using C = ECfg<D>;
     static_assert(C::SMEM_BYTES <= 232448, "shared memory budget");
-    static bool attr = false;
-    if (!attr) {
+    if (!t->attr_estep) {
         TC_CUDA_TRY(cudaFuncSetAttribute(estep_tc_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         TC_CUDA_TRY(cudaFuncSetAttribute(estep_tc_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr = true;
+        t->attr_estep = true;
     }
     auto kernel = t->estep_alt ? estep_tc_kernel<D, true> : estep_tc_kernel<D, false>;
     int threads = kEThreads, smem_bytes = C::SMEM_BYTES;
     if (t->estep_wg4) {
         using C4 = ECfg<D, 4>;
         static_assert(C4::SMEM_BYTES <= 232448, "shared memory budget");
-        static bool attr4 = false;
-        if (!attr4) {
+        if (!t->attr_estep4) {
             TC_CUDA_TRY(cudaFuncSetAttribute(estep_tc_kernel<D, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, C4::SMEM_BYTES));
-            attr4 = true;
+            t->attr_estep4 = true;
         }
         kernel = estep_tc_kernel<D, false, 4>;
         threads = C4::THREADS;
@@ -1316,11 +1336,10 @@ static int launch_mstep_d(TcState* t, int K, double* d_stats, cudaStream_t strea
     using C = MCfg<D>;
     static_assert(C::SMEM_BYTES <= 232448, "shared memory budget");
     static_assert(C::TMEM_COLS <= 512, "TMEM budget");
-    static bool attr = false;
-    if (!attr) {
+    if (!t->attr_mstep) {
         TC_CUDA_TRY(cudaFuncSetAttribute(mstep_tc_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         TC_CUDA_TRY(cudaFuncSetAttribute(mstep_tc_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr = true;
+        t->attr_mstep = true;
     }
     int gx = t->num_sms;
     int per = (t->n + gx - 1) / gx;

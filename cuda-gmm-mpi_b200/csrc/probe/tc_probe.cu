@@ -402,6 +402,46 @@ int main() {
                    repeats, bias, rms);
         }
     }
+    // ---- T7: rounding direction of the accumulation for NEGATIVE sums (toward zero or toward -inf?) ----
+    {
+        const int N = 64, K = 16;
+        std::vector<float> A((size_t)128 * K), B((size_t)N * K);
+        for (auto& v : A) v = -h2f(0.5f + (rand() % 1000) / 1000.0f);
+        for (auto& v : B) v = h2f(0.5f + (rand() % 1000) / 1000.0f);
+        for (int repeats : {1, 64}) {
+            Result r = run_mma(A, B, N, K, false, repeats);
+            double bias = 0;
+            for (int m = 0; m < 128; m++)
+                for (int n = 0; n < N; n++) {
+                    double p = 0;
+                    for (int k = 0; k < K; k++) p += (double)A[(size_t)m * K + k] * B[(size_t)n * K + k];
+                    double ref = p * repeats;
+                    bias += (r.D[(size_t)m * N + n] - ref) / fabs(ref);
+                }
+            printf("T7 negative sums, %d k-steps: mean (D - ref)/|ref| = %+.3e  (positive sums gave a negative value: < 0 here too = toward -inf, > 0 = toward zero)\n",
+                   repeats, bias / (128.0 * N));
+        }
+    }
+    // ---- T8: operands with few significant bits: is the accumulation exact while every partial sum fits 24 bits? ----
+    for (int bits : {5, 6, 7, 8}) {
+        const int N = 64, K = 16;
+        const float q = 1.0f / (float)(1 << bits);
+        std::vector<float> A((size_t)128 * K), B((size_t)N * K);
+        for (auto& v : A) v = q * (float)(rand() % (1 << bits)) * ((rand() & 1) ? 1.f : -1.f);      // multiples of q, |v| < 1
+        for (auto& v : B) v = q * (float)(rand() % (1 << bits));
+        for (int repeats : {8, 128}) {
+            Result r = run_mma(A, B, N, K, false, repeats);
+            double maxerr = 0;
+            for (int m = 0; m < 128; m++)
+                for (int n = 0; n < N; n++) {
+                    double p = 0;
+                    for (int k = 0; k < K; k++) p += (double)A[(size_t)m * K + k] * B[(size_t)n * K + k];
+                    maxerr = fmax(maxerr, fabs(r.D[(size_t)m * N + n] - p * repeats) / (q * q));
+                }
+            printf("T8 %d-bit operands, %3d k-steps (sum needs <= %d bits): max|err| = %g product quanta\n", bits, repeats,
+                   2 * bits + 4 + (repeats == 8 ? 3 : 7), maxerr);
+        }
+    }
     // ---- T3: MMA throughput (single CTA) ----
     for (int N : {64, 192, 256}) {
         const int K = 64;

@@ -96,14 +96,18 @@ int  gmm_comm_init(gmm_ctx*, int nranks, int rank, const char id[128]);
 int  gmm_comm_rank(const gmm_ctx*, int* rank, int* nranks);
 
 /* ---- options: the reference's compile-time #defines made runtime
- * (gaussian.h:23-38).  Known keys: "path" (GMM_PATH_*), "verbose",
- * "write_memberships" (1 = every E-step materialises memberships, as the
- * reference does; 0 = only gmm_estep()/gmm_get_clusters() do),
- * "host_threads" (threads of the host-side finalisation),
+ * (gaussian.h:23-38).  Known keys: "path" (GMM_PATH_*: both steps),
+ * "estep_path" / "mstep_path" (GMM_PATH_* for one step only, -1 = follow
+ * "path"), "verbose", "host_threads" (threads of the host-side
+ * finalisation), "profile" (0 = no per-phase CUDA-event timers inside the EM
+ * loop; gmm_get_profile then reports zeros for the device phases),
  * "mstep_gamma_split" (tensor M-step: 1 = responsibilities enter the MMA as
  * an FP16 hi/lo pair, 0 = as one round-to-nearest FP16 value (10 % faster
  * kernel, ~1.4e-4/sqrt(N_k) statistical error per cluster), 2 (default) =
- * pair whenever a cluster has fewer than 2048 events).                    */
+ * pair whenever a cluster has fewer than 2048 events).  Unknown keys are an
+ * error (GMM_ERR_ARG).  Every E-step materialises the memberships on the
+ * device (the reference's behaviour); they reach the host only through
+ * gmm_get_clusters / gmm_fit.                                              */
 int  gmm_set_option(gmm_ctx*, const char* key, double value);
 
 /* ---- operators (one per reference kernel group) ------------------------- */
@@ -151,7 +155,8 @@ int  gmm_em_iterations(gmm_ctx*, int K, int iters, float* loglik_out);
 /* Per-phase device/host time accumulated since the last reset, in ms
  * (replaces profile_t, gaussian.cu:76-106,967).
  * out[0]=estep out[1]=mstep out[2]=constants(host) out[3]=allreduce
- * out[4]=memcpy out[5]=fused e+m out[6]=iterations                          */
+ * out[4]=parameter finalisation + upload (host) out[5]=0 (reserved)
+ * out[6]=iterations                                                         */
 int  gmm_get_profile(gmm_ctx*, double out[8], int reset);
 
 /* Model-order reduction driver (gaussian.cu:479-960): for K = K0 .. stop:
