@@ -13,10 +13,13 @@
 //   GMM_PATH    0 auto, 1 SIMT kernels, 2 tcgen05 kernels
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -57,6 +60,17 @@ static int validate_arguments(int argc, char** argv, int* num_clusters, int* tar
     }
     return 0;
 }
+
+// All worker threads meet here once (the reference's `#pragma omp barrier` after its per-GPU setup, gaussian.cu:378).
+struct OneShotBarrier {
+    std::mutex m; std::condition_variable cv; int waiting = 0; const int total;
+    explicit OneShotBarrier(int n) : total(n) {}
+    void arrive_and_wait() {
+        std::unique_lock<std::mutex> lk(m);
+        if (++waiting == total) cv.notify_all();
+        else cv.wait(lk, [&] { return waiting == total; });
+    }
+};
 
 static int env_int(const char* name, int dflt) { const char* s = std::getenv(name); return s ? std::atoi(s) : dflt; }
 
@@ -114,6 +128,11 @@ extern "C" int gmm_main(int argc, char** argv) {
     std::vector<std::string> errs(G);
     std::vector<std::vector<double>> prof(G, std::vector<double>(8, 0.0));
 
+    // Every context is created (and checked) BEFORE any thread enters the communicator bootstrap: ncclCommInitRank
+    // needs all G ranks, so a rank that failed earlier (no sm_100 device, out of memory, bad GMM_PATH) would leave
+    // the others blocked for ever; the reference exits the whole process on a CUDA failure (CUDA_SAFE_CALL).
+    OneShotBarrier created(G);
+    std::atomic<int> setup_failed{0};
     auto worker = [&](int g) {
         long long begin, count;
         gmm_shard_range(N, G, g, &begin, &count);
@@ -121,7 +140,15 @@ extern "C" int gmm_main(int argc, char** argv) {
         int rc = gmm_create(&ctx, g, (int)count, D, K0, events + (size_t)begin * D, N, begin);
         if (!rc) rc = gmm_set_option(ctx, "path", path);
         if (!rc) rc = gmm_set_option(ctx, "verbose", print);
-        if (!rc) rc = gmm_comm_init(ctx, G, g, id);
+        if (rc) { errs[g] = gmm_last_error(); setup_failed.store(1); }
+        created.arrive_and_wait();
+        if (setup_failed.load()) {
+            if (!rc) { rc = GMM_ERR_STATE; errs[g] = "another GPU failed during setup"; }
+            rcs[g] = rc;
+            gmm_destroy(ctx);
+            return;
+        }
+        rc = gmm_comm_init(ctx, G, g, id);
         if (!rc) {
             HostClusters mine(K0, D, want_output ? (size_t)K0 * count : 0);
             rc = gmm_fit(ctx, K0, target, iters, iters, &mine.c, &ideal[g], &minr[g]);
@@ -142,7 +169,14 @@ extern "C" int gmm_main(int argc, char** argv) {
                 gmm_get_profile(ctx, prof[g].data(), 0);
             }
         }
-        if (rc) errs[g] = gmm_last_error();
+        if (rc) {
+            // an error between collectives on one rank would leave the peers inside ncclAllReduce: like the reference
+            // (CUDA_SAFE_CALL exits), the process ends here instead of joining threads that can never return
+            std::printf("ERROR (GPU %d): %s\n", g, gmm_last_error());
+            std::fflush(stdout);
+            if (G > 1) std::_Exit(rc == GMM_ERR_CUDA ? 255 : 1);
+            errs[g] = gmm_last_error();
+        }
         rcs[g] = rc;
         gmm_destroy(ctx);
     };

@@ -135,6 +135,8 @@ struct gmm_ctx {
     EventPool events;
     bool profile_phases = true;  // per-phase CUDA-event timers inside the EM loop (option "profile")
     double host_const_ms = 0, memcpy_ms = 0;
+    double fit_reduce_ms = 0, fit_seed_ms = 0, fit_save_ms = 0;   // gmm_fit phases (gmm_get_fit_profile)
+    long long mstep_pair = 0, mstep_single = 0;                   // tensor M-step launches by kernel template
     long long iterations = 0;
     TcState* tc = nullptr;       // tensor-core path state (kernels_tc.cuh)
     bool estep_tensor_ready = false;   // the tensor E-step operand of the current parameters is uploaded
@@ -344,8 +346,12 @@ static int run_mstep_accumulate(gmm_ctx* c, int K) {
     timer_begin(c, c->t_mstep);
     float min_nk = INFINITY;                       // cluster sizes of the parameters the responsibilities came from
     for (int k = 0; k < K; k++) min_nk = std::fmin(min_nk, c->host.N[k]);
-    int rc = use_tensor_mstep(c, K) ? tc_launch_mstep(c->tc, K, c->d_stats, c->stream, min_nk)
-                                    : launch_mstep_simt(c, K);
+    int rc;
+    if (use_tensor_mstep(c, K)) {
+        int pair = 0;
+        rc = tc_launch_mstep(c->tc, K, c->d_stats, c->stream, min_nk, &pair);
+        (pair ? c->mstep_pair : c->mstep_single)++;
+    } else rc = launch_mstep_simt(c, K);
     timer_end(c, c->t_mstep);
     return rc;
 }
@@ -786,12 +792,20 @@ int gmm_get_profile(gmm_ctx* c, double out[8], int reset) {
     cudaStreamSynchronize(c->stream);
     collect_all(c);
     out[0] = c->t_estep.total_ms; out[1] = c->t_mstep.total_ms; out[2] = c->host_const_ms;
-    out[3] = c->t_reduce.total_ms; out[4] = c->memcpy_ms; out[5] = c->t_fused.total_ms;
-    out[6] = (double)c->iterations; out[7] = 0;
+    out[3] = c->t_reduce.total_ms; out[4] = c->memcpy_ms; out[5] = (double)c->mstep_pair;
+    out[6] = (double)c->iterations; out[7] = (double)c->mstep_single;
     if (reset) {
         c->t_estep.total_ms = c->t_mstep.total_ms = c->t_reduce.total_ms = c->t_fused.total_ms = 0;
         c->host_const_ms = c->memcpy_ms = 0; c->iterations = 0;
+        c->mstep_pair = c->mstep_single = 0;
+        c->fit_reduce_ms = c->fit_seed_ms = c->fit_save_ms = 0;
     }
+    return GMM_OK;
+}
+
+int gmm_get_fit_profile(gmm_ctx* c, double out[4]) {
+    if (!c || !out) return fail(GMM_ERR_ARG, "gmm_get_fit_profile: bad argument");
+    out[0] = c->fit_reduce_ms; out[1] = c->fit_seed_ms; out[2] = c->fit_save_ms; out[3] = 0;
     return GMM_OK;
 }
 
@@ -804,7 +818,15 @@ int gmm_fit(gmm_ctx* c, int K0, int target_K, int min_iters, int max_iters, clus
     CUDA_TRY(cudaSetDevice(c->device));
     const int D = c->D;
     const int stop_number = target_K == 0 ? 1 : target_K;                  // gaussian.cu:177-181
-    if (int rc = gmm_seed(c, K0, nullptr)) return rc;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    {
+        const auto t0 = now();
+        if (int rc = gmm_seed(c, K0, nullptr)) return rc;
+        c->fit_seed_ms += ms_since(t0);
+    }
     const float epsilon = em_epsilon(D, c->n_global);
     float min_rissanen = 0;
     int ideal = K0;
@@ -816,14 +838,18 @@ int gmm_fit(gmm_ctx* c, int K0, int target_K, int min_iters, int max_iters, clus
         const float r = rissanen(likelihood, K, D, c->n_global);          // :826
         if (c->verbose && c->rank == 0) std::printf("K=%d loglik=%e Rissanen Score: %e\n", K, likelihood, r);
         if (K == K0 || (r < min_rissanen && target_K == 0) || K == target_K) {   // :839
+            const auto t0 = now();
             min_rissanen = r;
             ideal = K;
             copy_params(saved, &c->host, K, D);
             if (saved->memberships && c->n > 0)
                 CUDA_TRY(cudaMemcpyAsync(c->d_memb_saved, c->d_memb, sizeof(float) * (size_t)K * c->memb_pitch, cudaMemcpyDeviceToDevice, c->stream));
+            c->fit_save_ms += ms_since(t0);
         }
         if (K > stop_number) {                                            // :860-950
+            const auto t0 = now();
             K = reduce_order(&c->host, K, D, nullptr, nullptr, c->host_threads);
+            c->fit_reduce_ms += ms_since(t0);
             if (K < 1) break;
             c->memb_valid = false;
             if (int rc = upload_params(c, K)) return rc;

@@ -509,8 +509,8 @@ template <int D, int NWG = 2> struct ECfg {
     static constexpr int B_SG = CP * B_BLOCK;
     static constexpr int OFF_B = 0;
     static constexpr int OFF_A = OFF_B + MAXSG * B_SG;
-    static constexpr int OFF_CK = OFF_A + 2 * A_STAGE;        // float[64] constant + ln(pi)
-    static constexpr int OFF_EX = OFF_CK + 256;               // exchange: [2 parity][NWG][128] x (max, sum)
+    static constexpr int OFF_CK = OFF_A + 2 * A_STAGE;        // float2[64]: (constant + ln(pi)) * log2(e), -0.5 * log2(e) / scale_k^2
+    static constexpr int OFF_EX = OFF_CK + 512;               // exchange: [2 parity][NWG][128] x (max, sum)
     static constexpr int OFF_BAR = OFF_EX + 2 * NWG * 128 * 8;
     static constexpr int SMEM_BYTES = OFF_BAR + 512;
     static constexpr int THREADS = 256 + 128 * NWG;           // warpgroup 0, converters, NWG epilogue warpgroups
@@ -545,7 +545,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
     // ALT: the odd tiles' accumulators are announced on a second set of barriers, so that each epilogue warpgroup only
     // ever waits for the NEXT phase of a barrier (a parity wait cannot tell phase p from phase p + 2)
     uint64_t* acc_full_odd = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR + 384);   // [NBUF]
-    float* ck_s = reinterpret_cast<float*>(smem + C::OFF_CK);
+    float2* ck_s = reinterpret_cast<float2*>(smem + C::OFF_CK);
     float2* ex = reinterpret_cast<float2*>(smem + C::OFF_EX);
     float* sh_s = reinterpret_cast<float*>(smem + C::OFF_BAR + 128);   // [32] shift, [32] inverse scale
     float* isc_s = sh_s + 32;
@@ -561,7 +561,9 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
         if (ALT) for (int s = 0; s < C::NBUF; s++) mbar_init(&acc_full_odd[s], 1);
         fence_mbar_init();
     }
-    if (threadIdx.x < 64) ck_s[threadIdx.x] = ck[threadIdx.x] * 1.4426950408889634f;   // base-2 logits in the epilogue
+    // base-2 logits in the epilogue: l2 = ck * log2(e) + (-0.5 * log2(e) / scale_k^2) * |scale_k * y|^2   (the per-cluster
+    // power-of-two scale_k keeps the FP16 whitening factors in range whatever the cluster's width, see bimg_cluster)
+    if (threadIdx.x < 64) ck_s[threadIdx.x] = make_float2(ck[threadIdx.x] * 1.4426950408889634f, ck[64 + threadIdx.x]);
     if (threadIdx.x < D) { sh_s[threadIdx.x] = shift_f[threadIdx.x]; isc_s[threadIdx.x] = inv_scale_f[threadIdx.x]; }
     __syncthreads();
     if (threadIdx.x == 0) {                    // resident B operand: one TMA bulk copy per block
@@ -683,7 +685,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const int NB = NSG * C::CP;                            // blocks per tile; buffer of block j: j % NBUF (restarts per tile)
-        constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+        constexpr float kLn2 = 0.6931471805599453f;
         double ll_acc = 0.0;
         for (int it = g; it < my_tiles; it += 2) {
             const long long e = (long long)((int)blockIdx.x + it * (int)gridDim.x) * 128 + row;
@@ -732,7 +734,8 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                     for (int i = 0; i < C::GB; i++) {
                         float lo, hi;
                         asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(qs[i]));
-                        const float l = fmaf(-0.5f * kLog2e, lo + hi, ck_s[sg * C::GB + i]);
+                        const float2 cm = ck_s[sg * C::GB + i];
+                        const float l = fmaf(cm.y, lo + hi, cm.x);
                         lg[sg * C::GB + i] = l;
                         mx = fmaxf(mx, l);
                     }
@@ -780,7 +783,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
         uint32_t pf[C::NBUF];                                  // wait parity of acc_full[b]; b is static after unrolling
 #pragma unroll
         for (int b = 0; b < C::NBUF; b++) pf[b] = 0u;
-        constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+        constexpr float kLn2 = 0.6931471805599453f;
         for (int it = 0; it < my_tiles; it++) {
             const long long e = (long long)((int)blockIdx.x + it * (int)gridDim.x) * 128 + row;
             float lg[C::LPT];                                  // logits in base 2 (ck_s is pre-multiplied by log2 e)
@@ -827,7 +830,8 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                     }
 #pragma unroll
                     for (int i = 0; i < C::CW; i++) {
-                        const float l = fmaf(-0.5f * kLog2e, hsum2(qa[i], qb[i]), ck_s[sg * C::GB + wg * C::CW + i]);
+                        const float2 cm = ck_s[sg * C::GB + wg * C::CW + i];
+                        const float l = fmaf(cm.y, hsum2(qa[i], qb[i]), cm.x);
                         lg[sg * C::CW + i] = l;
                         mx = fmaxf(mx, l);
                     }
@@ -976,8 +980,8 @@ struct TcState {
     uint8_t* h_opnd = nullptr;       // pinned mirror
     cudaEvent_t ev_h2d = nullptr;    // the last operand copy has left the pinned buffer
     bool h2d_pending = false;
-    float* d_ck = nullptr;           // [e_ck_len]
-    float* h_ck = nullptr;           // pinned [e_ck_len]
+    float* d_ck = nullptr;           // [passes][ck 64 | mult 64]: additive constant and quadratic-form multiplier per cluster
+    float* h_ck = nullptr;           // pinned mirror
     float* d_den = nullptr;          // [passes][memb_pitch] per-pass log-denominators (Kmax > 64 only)
     int e_ck_len = 0;                // Kmax rounded up to whole passes of 64
     int e_NG = 0;
@@ -1053,7 +1057,7 @@ int tc_create(TcState** out, const float* d_x_aos, const float* d_x_soa, int n, 
         t->e_ck_len = passes * 64;
         t->bimg_bytes = (size_t)passes * pass_bytes_for(D);
         // one staging / device buffer [ck | B image]: the operand of an iteration travels in ONE H2D copy
-        const size_t ck_bytes = sizeof(float) * t->e_ck_len;         // 256 B per pass: keeps the image 16-byte aligned
+        const size_t ck_bytes = sizeof(float) * 2 * t->e_ck_len;     // 512 B per pass: keeps the image 16-byte aligned
         TC_CUDA_TRY(cudaMalloc(&t->d_opnd, ck_bytes + t->bimg_bytes));
         TC_CUDA_TRY(cudaMallocHost(&t->h_opnd, ck_bytes + t->bimg_bytes));
         t->d_ck = reinterpret_cast<float*>(t->d_opnd);
@@ -1181,44 +1185,58 @@ static int bimg_cluster(TcState* t, const clusters_t* host, int k, int K) {
             }
         }
         if (!ok) return 1;
+        // rows of W = Gc^T in the kernel's coordinates:  y_d = sum_j W'[d][j] z_j + v_d,  W'[d][j] = Gc[j][d] * scale_j (j >= d)
+        alignas(32) float wrow[D][D];
+        double vd[D];
+        float amax = 0.f;
         for (int d = 0; d < D; d++) {
-            // row d of W = Gc^T:  W[d][j] = Gc[j][d] (j >= d);  y_d = sum_j W'[d][j] z_j + v_d
-            double vd = 0.0;
-            alignas(32) float wrow[D];
-            float wmax = 0.f;
+            double v = 0.0;
             for (int j = 0; j < D; j++) {
                 const double w = (j >= d) ? Gc[j][d] : 0.0;
-                vd -= w * ((double)host->means[(size_t)k * D + j] - t->h_shift[j]);
-                wrow[j] = (float)(w * t->h_scale[j]);
-                wmax = std::fmax(wmax, std::fabs(wrow[j]));
+                v -= w * ((double)host->means[(size_t)k * D + j] - t->h_shift[j]);
+                wrow[d][j] = (float)(w * t->h_scale[j]);
+                amax = std::fmax(amax, std::fabs(wrow[d][j]));
             }
-            if (!(wmax < 6.0e4f)) bad = 2;
+            vd[d] = v;
+            amax = std::fmax(amax, (float)std::fabs(v));
+        }
+        if (!std::isfinite(amax)) return 2;
+        // Per-cluster power-of-two scale: the largest operand entry lands in [2^12, 2^13) whatever the width of the
+        // cluster (a cluster of relative width 1e-4 has factors ~1e4 - 1e5 and used to leave the FP16 range; a very wide
+        // one pushed its lo parts into the FP16 subnormals).  The epilogue divides the squared norm by scale^2 (exact).
+        int e2 = amax > 0.f ? 12 - std::ilogb(amax) : 0;
+        e2 = e2 > 40 ? 40 : (e2 < -40 ? -40 : e2);
+        for (int d = 0; d < D; d++) {
+            for (int j = 0; j < D; j++) wrow[d][j] = std::ldexp(wrow[d][j], e2);
+            vd[d] = std::ldexp(vd[d], e2);
             for (int c = 0; c < C::CP; c++) {
                 uint16_t *ph = rowp(d, c), *pl = rowp(d, C::CP + c);      // x (zh_c, zl_c) [aliased], x zh_c
 #if defined(__F16C__) && defined(__AVX__)
-                const __m256 w8 = _mm256_load_ps(wrow + 8 * c);
+                const __m256 w8 = _mm256_load_ps(&wrow[d][8 * c]);
                 const __m128i h8 = _mm256_cvtps_ph(w8, _MM_FROUND_TO_NEAREST_INT | _MM_FROUND_NO_EXC);
                 const __m256 l8 = _mm256_sub_ps(w8, _mm256_cvtph_ps(h8));  // exact: hi is w rounded to 11 bits
                 _mm_storeu_si128(reinterpret_cast<__m128i*>(ph), h8);
                 _mm_storeu_si128(reinterpret_cast<__m128i*>(pl), _mm256_cvtps_ph(l8, _MM_FROUND_TO_NEAREST_INT | _MM_FROUND_NO_EXC));
 #else
                 for (int e = 0; e < 8; e++) {
-                    const uint16_t wh = f2h_bits(wrow[8 * c + e]);
+                    const uint16_t wh = f2h_bits(wrow[d][8 * c + e]);
                     ph[e] = wh;
-                    pl[e] = f2h_bits(wrow[8 * c + e] - h2f_bits(wh));
+                    pl[e] = f2h_bits(wrow[d][8 * c + e] - h2f_bits(wh));
                 }
 #endif
             }
-            const float vf = (float)vd;
+            const float vf = (float)vd[d];
             if (!(std::fabs(vf) < 6.0e4f)) bad = 2;
             uint16_t* pv = rowp(d, 2 * C::CP);
             const uint16_t vh = f2h_bits(vf);
             std::memset(pv, 0, 16);
             pv[0] = vh;
-            pv[1] = f2h_bits((float)(vd - (double)h2f_bits(vh)));
+            pv[1] = f2h_bits((float)(vd[d] - (double)h2f_bits(vh)));
             if (C::NCHKB > 2 * C::CP + 1) std::memset(rowp(d, 2 * C::CP + 1), 0, 16);
         }
-        t->h_ck[k] = host->constant[k] + logf(host->pi[k]);  // additive term of estep1 (gaussian_kernel.cu:442)
+        float* ckp = t->h_ck + (size_t)(k / 64) * 128 + (k % 64);
+        ckp[0] = host->constant[k] + logf(host->pi[k]);      // additive term of estep1 (gaussian_kernel.cu:442)
+        ckp[64] = (float)std::ldexp(-0.5 * 1.4426950408889634, -2 * e2);
     }
     return bad;
 }
@@ -1240,7 +1258,11 @@ int tc_params_begin(TcState* t, int K, cudaStream_t stream) {
         TC_CUDA_TRY(cudaEventSynchronize(t->ev_h2d));
         t->h2d_pending = false;
     }
-    for (int k = K; k < t->e_ck_len; k++) t->h_ck[k] = -1e30f;
+    for (int k = K; k < t->e_ck_len; k++) {               // padding clusters: never win the log-sum-exp
+        float* ckp = t->h_ck + (size_t)(k / 64) * 128 + (k % 64);
+        ckp[0] = -1e30f;
+        ckp[64] = 0.f;
+    }
     return GMM_OK;
 }
 int tc_params_padded(const TcState*, int K) { return (K + 15) / 16 * 16; }
@@ -1252,7 +1274,7 @@ int tc_params_commit(TcState* t, int K, int bad, cudaStream_t stream) {
     t->e_NG = (K + 15) / 16;
     // only the supergroups in use travel (the image is contiguous per supergroup; 4 supergroups = 64 clusters)
     const size_t used = (size_t)t->e_NG * (pass_bytes_for(t->D) / 4);
-    TC_CUDA_TRY(cudaMemcpyAsync(t->d_opnd, t->h_opnd, sizeof(float) * t->e_ck_len + used, cudaMemcpyHostToDevice, stream));
+    TC_CUDA_TRY(cudaMemcpyAsync(t->d_opnd, t->h_opnd, sizeof(float) * 2 * t->e_ck_len + used, cudaMemcpyHostToDevice, stream));
     TC_CUDA_TRY(cudaEventRecord(t->ev_h2d, stream));
     t->h2d_pending = true;
     return GMM_OK;
@@ -1304,7 +1326,7 @@ static int launch_estep_d(TcState* t, int K, double* d_ll, cudaStream_t stream) 
     for (int p = 0; p < NP; p++) {
         const int Kp = K - 64 * p < 64 ? K - 64 * p : 64;
         kernel<<<grid, threads, smem_bytes, stream>>>(
-            t->d_x, t->d_bimg + (size_t)p * C::MAXSG * C::B_SG, t->d_ck + 64 * p, t->d_shift_f, t->d_inv_scale_f,
+            t->d_x, t->d_bimg + (size_t)p * C::MAXSG * C::B_SG, t->d_ck + 128 * p, t->d_shift_f, t->d_inv_scale_f,
             t->d_memb + (size_t)(64 * p) * t->memb_pitch, t->memb_pitch, t->n, Kp, (Kp + C::GB - 1) / C::GB, d_ll,
             NP > 1 ? t->d_den + (size_t)p * t->memb_pitch : nullptr);
         TC_CUDA_TRY(cudaGetLastError());
@@ -1332,7 +1354,7 @@ int tc_launch_estep(TcState* t, int K, double* d_ll, cudaStream_t stream) {
 constexpr float kGammaSplitMinN = 2048.0f;
 
 template <int D>
-static int launch_mstep_d(TcState* t, int K, double* d_stats, cudaStream_t stream, float min_nk) {
+static int launch_mstep_d(TcState* t, int K, double* d_stats, cudaStream_t stream, float min_nk, int* pair_out) {
     using C = MCfg<D>;
     static_assert(C::SMEM_BYTES <= 232448, "shared memory budget");
     static_assert(C::TMEM_COLS <= 512, "TMEM budget");
@@ -1353,6 +1375,7 @@ static int launch_mstep_d(TcState* t, int K, double* d_stats, cudaStream_t strea
     const size_t scratch_bytes = sizeof(double) * (size_t)gx * gy * C::MT * 128 * kNCL;
     if (t->scratch_clean_bytes < scratch_bytes) TC_CUDA_TRY(cudaMemsetAsync(t->d_scratch, 0, scratch_bytes, stream));
     const bool split = t->gamma_split == 1 || (t->gamma_split == 2 && !(min_nk >= kGammaSplitMinN));
+    if (pair_out) *pair_out = split ? 1 : 0;
     if (split)
         mstep_tc_kernel<D, true><<<grid, kMThreads, C::SMEM_BYTES, stream>>>(t->tm_x, t->tm_g, t->n, t->d_scratch, per);
     else
@@ -1374,16 +1397,16 @@ int tc_mstep_cleanup(TcState* t, cudaStream_t stream) {
     return GMM_OK;
 }
 
-int tc_launch_mstep(TcState* t, int K, double* d_stats, cudaStream_t stream, float min_nk) {
+int tc_launch_mstep(TcState* t, int K, double* d_stats, cudaStream_t stream, float min_nk, int* pair_out) {
     if (!t || !t->maps_ok) return fail(GMM_ERR_STATE, "tensor-core M-step not initialised for this shape");
     if (!t->have_shift) return fail(GMM_ERR_STATE, "tensor-core M-step needs gmm_seed (shift/scale) first");
     switch (t->D) {
-        case 4: return launch_mstep_d<4>(t, K, d_stats, stream, min_nk);
-        case 8: return launch_mstep_d<8>(t, K, d_stats, stream, min_nk);
-        case 12: return launch_mstep_d<12>(t, K, d_stats, stream, min_nk);
-        case 16: return launch_mstep_d<16>(t, K, d_stats, stream, min_nk);
-        case 20: return launch_mstep_d<20>(t, K, d_stats, stream, min_nk);
-        case 24: return launch_mstep_d<24>(t, K, d_stats, stream, min_nk);
+        case 4: return launch_mstep_d<4>(t, K, d_stats, stream, min_nk, pair_out);
+        case 8: return launch_mstep_d<8>(t, K, d_stats, stream, min_nk, pair_out);
+        case 12: return launch_mstep_d<12>(t, K, d_stats, stream, min_nk, pair_out);
+        case 16: return launch_mstep_d<16>(t, K, d_stats, stream, min_nk, pair_out);
+        case 20: return launch_mstep_d<20>(t, K, d_stats, stream, min_nk, pair_out);
+        case 24: return launch_mstep_d<24>(t, K, d_stats, stream, min_nk, pair_out);
         default: return fail(GMM_ERR_ARG, "tensor-core M-step: unsupported D");
     }
 }

@@ -34,7 +34,8 @@ int  tc_params_commit(TcState*, int K, int bad, cudaStream_t stream);
 int  tc_launch_estep(TcState*, int K, double* d_ll, cudaStream_t stream);
 // Accumulates sum_n g[k][n] * phi_f(x_n - shift) into d_stats[k*F + f] (double, original units).
 // min_nk: smallest N_k of the current parameters (global, all ranks); only read under gamma-split mode 2.
-int  tc_launch_mstep(TcState*, int K, double* d_stats, cudaStream_t stream, float min_nk);
+// *pair_out (optional): 1 when the FP16-pair kernel (three products) ran, 0 for the single-FP16 one (two products).
+int  tc_launch_mstep(TcState*, int K, double* d_stats, cudaStream_t stream, float min_nk, int* pair_out = nullptr);
 // Zeroes the per-CTA scratch of the last tc_launch_mstep for the next one; meant to be enqueued behind the D2H copy
 // of the statistics so that it runs while the host finalises.
 int  tc_mstep_cleanup(TcState*, cudaStream_t stream);

@@ -74,6 +74,7 @@ def load_library():
     L.gmm_em.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, _FP, _IP]
     L.gmm_em_iterations.argtypes = [C.c_void_p, C.c_int, C.c_int, _FP]
     L.gmm_get_profile.argtypes = [C.c_void_p, _DP, C.c_int]
+    L.gmm_get_fit_profile.argtypes = [C.c_void_p, _DP]
     L.gmm_fit.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _CP, _IP, _FP]
     L.gmm_host_invert.argtypes = [_FP, C.c_int, _FP, C.c_int]
     L.gmm_stats_len.argtypes = [C.c_int, C.c_int]
@@ -264,8 +265,19 @@ class Engine:
     def profile(self, reset=False):
         out = (C.c_double * 8)()
         _check(self.lib.gmm_get_profile(self.h, out, int(reset)))
-        keys = ("estep_ms", "mstep_ms", "constants_host_ms", "allreduce_ms", "upload_ms", "fused_ms", "iterations")
-        return dict(zip(keys, list(out)[:7]))
+        keys = ("estep_ms", "mstep_ms", "constants_host_ms", "allreduce_ms", "upload_ms", "mstep_pair_launches", "iterations",
+                "mstep_single_launches")
+        return dict(zip(keys, list(out)[:8]))
+
+    def fit_profile(self):
+        out = (C.c_double * 4)()
+        _check(self.lib.gmm_get_fit_profile(self.h, out))
+        return dict(reduce_order_ms=out[0], seed_ms=out[1], save_ms=out[2])
+
+    def comm_rank(self):
+        r, n = C.c_int(), C.c_int()
+        _check(self.lib.gmm_comm_rank(self.h, C.byref(r), C.byref(n)))
+        return r.value, n.value
 
     def fit(self, K0, target_K, min_iters, max_iters, saved=None, with_memberships=False):
         saved = saved or self.new_clusters(with_memberships)

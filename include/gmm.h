@@ -155,9 +155,15 @@ int  gmm_em_iterations(gmm_ctx*, int K, int iters, float* loglik_out);
 /* Per-phase device/host time accumulated since the last reset, in ms
  * (replaces profile_t, gaussian.cu:76-106,967).
  * out[0]=estep out[1]=mstep out[2]=constants(host) out[3]=allreduce
- * out[4]=parameter finalisation + upload (host) out[5]=0 (reserved)
- * out[6]=iterations                                                         */
+ * out[4]=parameter finalisation + upload (host) out[6]=iterations
+ * out[5] / out[7] = tensor M-step launches with the responsibilities as an
+ * FP16 hi/lo pair (three MMA products) / as one FP16 value (two products)   */
 int  gmm_get_profile(gmm_ctx*, double out[8], int reset);
+
+/* Host-side phases of gmm_fit since the last gmm_get_profile(reset=1), in ms:
+ * out[0]=order reduction (gaussian.cu:860-907: empties, pair search, merge)
+ * out[1]=seeding (:390-452) out[2]=saving the best configuration (:839-851) */
+int  gmm_get_fit_profile(gmm_ctx*, double out[4]);
 
 /* Model-order reduction driver (gaussian.cu:479-960): for K = K0 .. stop:
  * EM, Rissanen score, save-best, drop empty clusters, merge closest pair.

@@ -276,14 +276,19 @@ static void block_range(int N, int nblocks, int b, int* start, int* stop) {
  * Full D x D double loop, exactly as written (:435-439).
  * ------------------------------------------------------------------------- */
 void oracle_estep1(const float* soa, int N, int D, int K, clusters_t* c) {
-#pragma omp parallel for schedule(static)
-    for (int k = 0; k < K; k++) {
+    /* every (cluster, event) value is independent: clusters x event chunks are spread over the threads
+     * (the arithmetic per value is the reference's, whatever the decomposition) */
+    const int EB = 8192, nb = (N + EB - 1) / EB;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int k = 0; k < K; k++)
+      for (int b = 0; b < nb; b++) {
         const float* means = c->means + (size_t)k * D;
         const float* Rinv = c->Rinv + (size_t)k * D * D;
         real cluster_pi = c->pi[k];
         real constant = c->constant[k];
         real logpi = r_log(cluster_pi);
-        for (int e = 0; e < N; e++) {
+        const int e1 = (b + 1) * EB < N ? (b + 1) * EB : N;
+        for (int e = b * EB; e < e1; e++) {
             real like = 0;
             for (int i = 0; i < D; i++)
                 for (int j = 0; j < D; j++)
@@ -301,24 +306,35 @@ void oracle_estep1(const float* soa, int N, int D, int K, clusters_t* c) {
  * ------------------------------------------------------------------------- */
 float oracle_estep2(int N, int K, clusters_t* c) {
     float partial[NUM_BLOCKS];
+    /* pass 1 (independent per event, spread over all threads): denominators + normalisation in place;
+     * pass 2: the per-block / per-thread partial sums of the denominators in the reference's order */
+    real* den_all = (real*)malloc(sizeof(real) * (size_t)(N > 0 ? N : 1));
+    const int EB = 4096, nb = (N + EB - 1) / EB;
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < nb; b++) {
+        const int e1 = (b + 1) * EB < N ? (b + 1) * EB : N;
+        for (int e = b * EB; e < e1; e++) {
+            real mx = c->memberships[e];
+            for (int k = 1; k < K; k++) mx = r_max(mx, (real)c->memberships[(size_t)k * N + e]);
+            real den = 0;
+            for (int k = 0; k < K; k++) den += r_exp((real)c->memberships[(size_t)k * N + e] - mx);
+            den = mx + r_log(den);
+            den_all[e] = den;
+            for (int k = 0; k < K; k++)
+                c->memberships[(size_t)k * N + e] = (float)r_exp((real)c->memberships[(size_t)k * N + e] - den);
+        }
+    }
 #pragma omp parallel for schedule(static)
     for (int b = 0; b < NUM_BLOCKS; b++) {
         int start, stop;
         block_range(N, NUM_BLOCKS, b, &start, &stop);
         real thread_ll[NUM_THREADS_ESTEP];
         for (int t = 0; t < NUM_THREADS_ESTEP; t++) thread_ll[t] = 0;
-        for (int e = start; e < stop; e++) {
-            real mx = c->memberships[e];
-            for (int k = 1; k < K; k++) mx = r_max(mx, (real)c->memberships[(size_t)k * N + e]);
-            real den = 0;
-            for (int k = 0; k < K; k++) den += r_exp((real)c->memberships[(size_t)k * N + e] - mx);
-            den = mx + r_log(den);
-            thread_ll[(e - start) % NUM_THREADS_ESTEP] += den;     /* thread tid owns start+tid+512*i */
-            for (int k = 0; k < K; k++)
-                c->memberships[(size_t)k * N + e] = (float)r_exp((real)c->memberships[(size_t)k * N + e] - den);
-        }
+        for (int e = start; e < stop; e++)
+            thread_ll[(e - start) % NUM_THREADS_ESTEP] += den_all[e];     /* thread tid owns start+tid+512*i */
         partial[b] = (float)butterfly_sum(thread_ll, NUM_THREADS_ESTEP);
     }
+    free(den_all);
     float likelihood = 0.0;
     for (int i = 0; i < NUM_BLOCKS; i++) likelihood += partial[i];
     return likelihood;

@@ -134,6 +134,33 @@ def test_estep_tensor_path_large(loaded, oracle64, N, D, K):
     assert abs(ll - ll_ref) <= 1e-5 * abs(ll_ref)
 
 
+@pytest.mark.parametrize("sigma", [1e-3, 1e-4, 1e-5])
+@pytest.mark.parametrize("N,D,K", [(20_000, 24, 64), (9_001, 16, 9), (8_000, 8, 70)])
+def test_estep_tensor_tight_and_wide_clusters(loaded, oracle64, N, D, K, sigma):
+    """Clusters far narrower than the data (whitening factors 1e3 .. 1e6 in the kernel's standardised coordinates,
+    beyond the FP16 range without the per-cluster power-of-two operand scale) next to ordinary and very wide ones:
+    GMM_PATH_TENSOR must evaluate them itself (no SIMT fallback) at the per-operator bar."""
+    pkg = loaded
+    ev = pkg.synth.make_blobs(N, D, min(K, 8), seed=500 + D)
+    ref = fitted_params(pkg, oracle64, ev, K)
+    rng = np.random.default_rng(K)
+    for k, idx in ((0, 123), (K - 1, 4567)):                 # two needle clusters sitting on events
+        ref.means[k] = ev[idx] + rng.normal(0, sigma, D).astype(np.float32)
+        ref.R[k] = np.eye(D, dtype=np.float32) * np.float32(sigma * sigma)
+        ref.N[k] = 3.0
+    ref.R[1] = np.eye(D, dtype=np.float32) * np.float32(400.0)   # and one far wider than the data
+    oracle64.constants(ref, K)
+    with pkg.Engine(ev, K) as eng:
+        eng.set_option("path", pkg.PATH_TENSOR)
+        eng.set_clusters(K, ref)
+        ll = eng.estep(K)
+        got = eng.get_clusters(K, with_memberships=True)
+    ll_ref = oracle64.estep(oracle64.transpose(ev), ref, K)
+    assert_memb_close(got.memberships, ref.memberships)
+    assert ref.memberships[0, 123] > 0.5 and ref.memberships[K - 1, 4567] > 0.5      # the needles do capture their events
+    assert abs(ll - ll_ref) <= 1e-5 * abs(ll_ref)
+
+
 @pytest.mark.parametrize("N,D,K", [(200_000, 24, 64), (150_001, 16, 32), (100_000, 4, 8), (70_000, 24, 100)])
 def test_mstep_tensor_path_large(loaded, oracle64, N, D, K):
     """The tcgen05 M-step (GMM_PATH_TENSOR) on enough events to exercise several TMEM
