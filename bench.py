@@ -409,11 +409,12 @@ def main():
     m_tfs = m_flops / (mstep_ms * 1e-3) / 1e12 if mstep_ms > 0 else 0.0
     tensor_m = args.path != "simt" and D in (4, 8, 12, 16, 20, 24)
     launches_per_step = 3 if tensor_m else 2
-    n_pair, n_single = int(prof.get("mstep_pair_launches", 0)), int(prof.get("mstep_single_launches", 0))
+    n_tensor, n_simt = int(prof.get("mstep_tensor_launches", 0)), int(prof.get("mstep_simt_launches", 0))
     F = 1 + D + D * (D + 1) // 2
     mt_rows = (F + 127) // 128 * 128
-    products = (3 * n_pair + 2 * n_single) / max(1, n_pair + n_single) if tensor_m else 0
-    exec_flops = 2.0 * count * mt_rows * ((K + 63) // 64 * 64) * products
+    # executed MMA flops per launch of mstep_tc_kernel: per 16 events and feature tile one M=128,N=128 (ph x [gh;gl]) and one
+    # M=128,N=64 (pl x gh) MMA = 3 products of the padded (mt_rows x 64-cluster) tile
+    exec_flops = 2.0 * count * mt_rows * ((K + 63) // 64 * 64) * 3 if n_tensor else 0.0
     traffic = traffic_m = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath) and world == 1:
@@ -429,8 +430,9 @@ def main():
                           peak_source=peaks["source"] + " dense bf16/fp16 sustained (the kernel issues kind::f16 MMAs)",
                           ms_per_launch=mstep_ms, algorithmic_flops_per_launch=m_flops,
                           executed_mma_flops_per_launch=exec_flops, executed_tflops=exec_flops / (mstep_ms * 1e-3) / 1e12 if mstep_ms > 0 else 0.0,
-                          kernel_template=dict(pair_fp16_responsibilities=n_pair, single_fp16_responsibilities=n_single,
-                                               note="launch counts in the timed region: mstep_tc_kernel<D,true> (3 products) / <D,false> (2 products)"))
+                          kernel=dict(mstep_tc_kernel_launches=n_tensor, mstep_simt_kernel_launches=n_simt,
+                                      note="launch counts in the timed region; mstep_tc_kernel = fixed-point leading parts (exact TMEM "
+                                           "accumulation) + FP16 remainders, three products per element"))
 
     # ---- config 5: model-order reduction K0=128 -> 16 (gmm_fit) on the same GPUs ----
     config5 = None

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <thread>
 #include <vector>
@@ -136,7 +137,7 @@ struct gmm_ctx {
     bool profile_phases = true;  // per-phase CUDA-event timers inside the EM loop (option "profile")
     double host_const_ms = 0, memcpy_ms = 0;
     double fit_reduce_ms = 0, fit_seed_ms = 0, fit_save_ms = 0;   // gmm_fit phases (gmm_get_fit_profile)
-    long long mstep_pair = 0, mstep_single = 0;                   // tensor M-step launches by kernel template
+    long long mstep_tensor = 0, mstep_simt = 0;                   // M-step launches by kernel
     long long iterations = 0;
     TcState* tc = nullptr;       // tensor-core path state (kernels_tc.cuh)
     bool estep_tensor_ready = false;   // the tensor E-step operand of the current parameters is uploaded
@@ -197,11 +198,17 @@ static int default_host_threads(int ranks_on_box) {
 static int estep_path_of(const gmm_ctx* c) { return c->estep_path >= 0 ? c->estep_path : c->path; }
 static int mstep_path_of(const gmm_ctx* c) { return c->mstep_path >= 0 ? c->mstep_path : c->path; }
 static bool use_tensor_estep(const gmm_ctx* c, int K) { return estep_path_of(c) != GMM_PATH_SIMT && c->n > 0 && tc_estep_supported(c->D, K); }
-static bool use_tensor_mstep(const gmm_ctx* c, int K) { return mstep_path_of(c) != GMM_PATH_SIMT && c->n > 0 && tc_mstep_supported(c->D, K); }
+// (the tensor M-step also needs the data range to fit its fixed-point operand budget: known once the moments are)
+static bool use_tensor_mstep(const gmm_ctx* c, int K) {
+    return mstep_path_of(c) != GMM_PATH_SIMT && c->n > 0 && tc_mstep_supported(c->D, K) && (!c->have_shift || tc_mstep_ready(c->tc));
+}
 // GMM_PATH_TENSOR never degrades silently: the M-step (the covariance contraction) must be covered.
 static int check_path(const gmm_ctx* c, int K) {
     if (mstep_path_of(c) == GMM_PATH_TENSOR && !tc_mstep_supported(c->D, K))
         return fail(GMM_ERR_ARG, "GMM_PATH_TENSOR requested but the tcgen05 kernels do not cover this (D, K)");
+    if (mstep_path_of(c) == GMM_PATH_TENSOR && c->n > 0 && c->have_shift && !tc_mstep_ready(c->tc))
+        return fail(GMM_ERR_ARG, "GMM_PATH_TENSOR requested but the data range (outliers beyond 64 standard deviations) exceeds the "
+                                 "tensor M-step's fixed-point operand budget");
     return GMM_OK;
 }
 
@@ -219,7 +226,9 @@ static int upload_params(gmm_ctx* c, int K, bool with_constants = false, bool wi
     c->estep_tensor_ready = false;
     if (use_tensor_estep(c, K)) {
         if (int rc = ensure_moments(c)) return rc;
-        int rc = tc_params_begin(c->tc, K, c->stream);
+        // events further than 2^14 global standard deviations from the centre would overflow the FP16 event operand
+        int rc = tc_estep_range_ok(c->tc) ? tc_params_begin(c->tc, K, c->stream)
+                                          : fail(GMM_ERR_STATE, "tensor E-step: the data range exceeds the FP16 event operand");
         if (rc == GMM_OK) {
             if (with_finalize)                     // pi needs every N[k] = (float)S0 before the per-cluster loop
                 for (int k = 0; k < K; k++) c->host.N[k] = (float)c->h_stats[(size_t)k * c->F];
@@ -344,14 +353,9 @@ static int run_mstep_accumulate(gmm_ctx* c, int K) {
     if (c->stats_clean_K != K) CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(double) * (size_t)K * c->F, c->stream));
     c->stats_clean_K = 0;
     timer_begin(c, c->t_mstep);
-    float min_nk = INFINITY;                       // cluster sizes of the parameters the responsibilities came from
-    for (int k = 0; k < K; k++) min_nk = std::fmin(min_nk, c->host.N[k]);
     int rc;
-    if (use_tensor_mstep(c, K)) {
-        int pair = 0;
-        rc = tc_launch_mstep(c->tc, K, c->d_stats, c->stream, min_nk, &pair);
-        (pair ? c->mstep_pair : c->mstep_single)++;
-    } else rc = launch_mstep_simt(c, K);
+    if (use_tensor_mstep(c, K)) { rc = tc_launch_mstep(c->tc, K, c->d_stats, c->stream); c->mstep_tensor++; }
+    else { rc = launch_mstep_simt(c, K); c->mstep_simt++; }
     timer_end(c, c->t_mstep);
     return rc;
 }
@@ -369,7 +373,6 @@ static int reduce_stats_to_host(gmm_ctx* c, int K) {
     timer_end(c, c->t_reduce);
     CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(double) * len, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaEventRecord(c->ev_stats, c->stream));
-    if (int rc = tc_mstep_cleanup(c->tc, c->stream)) return rc;     // runs while the host finalises
     CUDA_TRY(cudaEventSynchronize(c->ev_stats));
     return GMM_OK;
 }
@@ -388,7 +391,11 @@ static int ensure_moments(gmm_ctx* c) {
     if (c->have_shift) return GMM_OK;
     const int D = c->D;
     c->stats_clean_K = 0;
-    CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(double) * 2 * D, c->stream));
+    // d_stats[0..D) sum x, [D..2D) sum x^2, [2D..3D) max x, [3D..4D) max (-x)
+    std::vector<double> init(4 * (size_t)D, 0.0);
+    for (int d = 0; d < 2 * D; d++) init[2 * D + d] = -std::numeric_limits<double>::max();
+    if (4 * (size_t)D > (size_t)c->Kmax * c->F + 1) return fail(GMM_ERR_STATE, "stats buffer too small for the column moments");
+    CUDA_TRY(cudaMemcpyAsync(c->d_stats, init.data(), sizeof(double) * 4 * D, cudaMemcpyHostToDevice, c->stream));
     if (c->n > 0) {
         dim3 grid(std::min(4 * c->num_sms, (c->n + 255) / 256), D);
         column_moments_kernel<<<grid, 256, 0, c->stream>>>(c->d_x_soa, c->memb_pitch, c->n, D, c->d_stats);
@@ -396,19 +403,23 @@ static int ensure_moments(gmm_ctx* c) {
     }
     if (c->nranks > 1) {
         ncclResult_t r = nccl().AllReduce(c->d_stats, c->d_stats, 2 * D, ncclDouble, ncclSum, c->comm, c->stream);
+        if (r == ncclSuccess) r = nccl().AllReduce(c->d_stats + 2 * D, c->d_stats + 2 * D, 2 * D, ncclDouble, ncclMax, c->comm, c->stream);
         if (r != ncclSuccess) return fail(GMM_ERR_NCCL, std::string("ncclAllReduce: ") + nccl().GetErrorString(r));
     }
-    CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(double) * 2 * D, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(double) * 4 * D, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    double xmin[GMM_MAX_DIMENSIONS], xmax[GMM_MAX_DIMENSIONS];
     for (int d = 0; d < D; d++) {
         c->sum_x[d] = c->h_stats[d];
         c->sum_x2[d] = c->h_stats[D + d];
+        xmax[d] = c->h_stats[2 * D + d];
+        xmin[d] = -c->h_stats[3 * D + d];
         const double mean = c->sum_x[d] / (double)c->n_global;
         const double var = c->sum_x2[d] / (double)c->n_global - mean * mean;
         c->shift[d] = mean;
         c->scale[d] = var > 0 ? std::sqrt(var) : 1.0;
     }
-    if (int rc = tc_set_shift_scale(c->tc, c->shift, c->scale, c->stream)) return rc;   // rounds shift to float in place
+    if (int rc = tc_set_shift_scale(c->tc, c->shift, c->scale, xmin, xmax, c->stream)) return rc;   // rounds shift to float in place
     CUDA_TRY(cudaMemcpyAsync(c->d_shift, c->shift, sizeof(double) * D, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->have_shift = true;
@@ -583,7 +594,6 @@ int gmm_set_option(gmm_ctx* c, const char* key, double value) {
         c->host_threads_fixed = true;
         tc_set_host_threads(c->tc, c->host_threads);
     }
-    else if (k == "mstep_gamma_split") { tc_set_gamma_split(c->tc, (int)value); }
     else if (k == "estep_path" || k == "mstep_path") {
         const int p = (int)value;
         if (p < -1 || p > GMM_PATH_TENSOR) return fail(GMM_ERR_ARG, "gmm_set_option: bad path");
@@ -792,12 +802,12 @@ int gmm_get_profile(gmm_ctx* c, double out[8], int reset) {
     cudaStreamSynchronize(c->stream);
     collect_all(c);
     out[0] = c->t_estep.total_ms; out[1] = c->t_mstep.total_ms; out[2] = c->host_const_ms;
-    out[3] = c->t_reduce.total_ms; out[4] = c->memcpy_ms; out[5] = (double)c->mstep_pair;
-    out[6] = (double)c->iterations; out[7] = (double)c->mstep_single;
+    out[3] = c->t_reduce.total_ms; out[4] = c->memcpy_ms; out[5] = (double)c->mstep_tensor;
+    out[6] = (double)c->iterations; out[7] = (double)c->mstep_simt;
     if (reset) {
         c->t_estep.total_ms = c->t_mstep.total_ms = c->t_reduce.total_ms = c->t_fused.total_ms = 0;
         c->host_const_ms = c->memcpy_ms = 0; c->iterations = 0;
-        c->mstep_pair = c->mstep_single = 0;
+        c->mstep_tensor = c->mstep_simt = 0;
         c->fit_reduce_ms = c->fit_seed_ms = c->fit_save_ms = 0;
     }
     return GMM_OK;

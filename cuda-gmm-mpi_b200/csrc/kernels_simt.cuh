@@ -225,27 +225,48 @@ __global__ void transpose_aos_to_soa_kernel(const float* __restrict__ aos, float
     }
 }
 
-// Column sums for seeding: out[d] += sum x, out[D+d] += sum x^2 (double).
+// Column sums for seeding: out[d] += sum x, out[D+d] += sum x^2 (double); column extremes:
+// out[2D+d] = max x, out[3D+d] = max (-x) (initialised to -DBL_MAX by the caller).
 // Replaces mvtmeans / averageVariance (gaussian_kernel.cu:54-102), which scan
 // the events serially with one thread per dimension.
+__device__ __forceinline__ void atomic_max_double(double* addr, double v) {
+    unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+    unsigned long long old = *a;
+    while (__longlong_as_double((long long)old) < v) {
+        const unsigned long long assumed = old;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+        if (old == assumed) break;
+    }
+}
 __global__ void column_moments_kernel(const float* __restrict__ xs, size_t xpitch, int n, int D, double* __restrict__ out) {
     const int d = blockIdx.y;
     const float* col = xs + (size_t)d * xpitch;
     double s1 = 0, s2 = 0;
+    float mx = -INFINITY, mn = INFINITY;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-        const double v = col[e];
+        const float x = col[e];
+        const double v = x;
         s1 += v;
         s2 += v * v;
+        mx = fmaxf(mx, x);
+        mn = fminf(mn, x);
     }
     __shared__ double r1[8], r2[8];
+    __shared__ float r3[8], r4[8];
     s1 = warp_sum(s1); s2 = warp_sum(s2);
-    if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = s1; r2[threadIdx.x >> 5] = s2; }
+    for (int o = 16; o > 0; o >>= 1) { mx = fmaxf(mx, __shfl_down_sync(0xffffffffu, mx, o)); mn = fminf(mn, __shfl_down_sync(0xffffffffu, mn, o)); }
+    if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = s1; r2[threadIdx.x >> 5] = s2; r3[threadIdx.x >> 5] = mx; r4[threadIdx.x >> 5] = mn; }
     __syncthreads();
     if (threadIdx.x == 0) {
         double a = 0, b = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { a += r1[w]; b += r2[w]; }
+        float hi = -INFINITY, lo = INFINITY;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { a += r1[w]; b += r2[w]; hi = fmaxf(hi, r3[w]); lo = fminf(lo, r4[w]); }
         atomicAdd(&out[d], a);
         atomicAdd(&out[D + d], b);
+        if (hi >= lo) {                                      // this block saw at least one event
+            atomic_max_double(&out[2 * D + d], (double)hi);
+            atomic_max_double(&out[3 * D + d], -(double)lo);
+        }
     }
 }
 

@@ -7,23 +7,40 @@
 //
 // with the per-event feature vector phi = [1, z_d, z_i z_j (i>=j)] (F = 1+D+D(D+1)/2
 // rows, shared by all clusters) as the A operand and the responsibilities as the
-// B operand; FP32 accumulation in TMEM.  Both operands are split into FP16
-// hi + lo parts (22 significant bits) and the three significant products
-// (hi*hi, lo*hi, hi*lo) are accumulated, i.e. 3 MMA passes at FP16 rate.
+// B operand; FP32 accumulation in TMEM.
+//
+// Operand arithmetic (round 2).  The FP32 accumulation in TMEM truncates toward zero (tc_probe T2/T7) — but it
+// is EXACT as long as every partial sum is a multiple of one quantum and fits 24 bits (tc_probe T8).  The
+// operands are therefore split into a FIXED-POINT leading part and a small remainder:
+//     phi_f = ph + pl,   ph = q_f * round(phi_f / q_f),   |ph| <= 2^9 q_f      (q_f: power of two per feature row,
+//                                                                              from the data's largest |z_d|)
+//     g     = gh + gl,   gh = 2^-8 * round(2^8 g)   (0 .. 256 quanta)
+// (both by a magic-number add: no conversion round trip), and the products go to two accumulators per
+// 128-row feature tile:
+//     columns [0, 64):    sum ph * gh                 — every product a multiple of q_f 2^-8, at most 2^17 quanta;
+//                                                       128 events per chain: <= 2^24 quanta: NO rounding at all
+//     columns [64, 128):  sum ph * gl + pl * gh       — 2^-8 of the magnitude; its truncation bias (~1e-6 relative
+//                                                       to itself) is 1e-8 .. 1e-9 of the statistic
+// The raw-moment cancellation |mu - shift|^2 / sigma^2 ~ 100 that amplified the old split's systematic error
+// (1.5e-3 on responsibilities after 100 EM iterations) now multiplies unbiased rounding noise only.
+// With B = [gh ; gl] stacked as ONE N = 128 operand, ph x [gh ; gl] is a single MMA at the tensor pipe's math
+// rate (64 cycles; N = 64 runs at 49.8, operand-fetch bound) that fills both column groups; pl x gh (N = 64)
+// adds into the second group: 114 instead of 149 cycles per (tile, k-step) and 14 instead of 18 KB of operand
+// fetch.
 //
 // Dataflow per CTA (persistent over a contiguous range of events, 512 threads):
 //   warp 0      TMA producer: tile [D][32 events] of the pre-standardised SoA copy z and raw
 //               responsibility tile [64 clusters][32 events] (2-D tensor maps, SWIZZLE_128B for
 //               the latter, zero fill out of bounds)
 //   warps 4-11  operand builders (two warpgroups on alternate tiles): form the products, split
-//               hi/lo, write the UMMA operand images (SWIZZLE_NONE core-matrix layout)
-//   warp 1      MMA issuer: 3 x 2 x MT tcgen05.mma (M=128, N=64, K=16) per 32 events
-//   warps 12-15 flush: every 128 events the TMEM accumulators are added (FP32, round to
-//               nearest) into register-resident partial sums (setmaxnreg gives this
-//               warpgroup 240 registers) — the TMEM accumulation itself truncates:
-//               measured bias -1e-7 per MMA step (profiles/tc_probe_r1.txt), so the
-//               chains are kept to 24 steps; every 2048 events the partial sums move into
-//               per-thread double slots of an L2-resident scratch (RED.ADD.F64)
+//               them, write the UMMA operand images (SWIZZLE_NONE core-matrix layout)
+//   warp 1      MMA issuer: per 32 events and feature tile 2 x (M=128, N=128, K=16) + 2 x (M=128, N=64, K=16)
+//   warps 12-15 flush: accumulators are SINGLE-buffered (3 tiles x 128 columns at D = 24); each feature tile
+//               is drained every 128 events, the three tiles staggered by one sub-tile so that a drain
+//               (TMEM -> registers, FP32 round-to-nearest adds into 192 register-resident partial sums per
+//               thread) overlaps the MMAs of the other tiles.  The partial sums stay in registers for the whole
+//               CTA range and are written ONCE (no scratch zeroing, no atomics: round 1 moved 1.7 GB of
+//               RED.ADD.F64 traffic per launch).
 // A second tiny kernel reduces the per-CTA partials in double and un-scales.
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -58,56 +75,24 @@ using namespace ptx;
 // ---------------------------------------------------------------------------
 // M-step kernel configuration
 // ---------------------------------------------------------------------------
-#ifndef GMM_CHUNKSUB
-#define GMM_CHUNKSUB 4
-#endif
-#ifndef GMM_SPILL
-#define GMM_SPILL 16
-#endif
 constexpr int kTE = 32;          // events per sub-tile (MMA K extent per operand part)
-constexpr int kNCL = 64;         // clusters per CTA pass (MMA N)
-// Pipeline depth.  GMM_MSTEP_NST / GMM_MSTEP_NRAW / GMM_MSTEP_TRIM are build-time experiment knobs (defaults = the validated
-// configuration): a fourth operand stage fits when the phi images are trimmed to their real rows and two raw stages
-// are given up (D = 24: 223.7 KB) — the builders were measured waiting on op_empty once per tile (profiles/).
-#ifndef GMM_MSTEP_NST
-#define GMM_MSTEP_NST 3
-#endif
-#ifndef GMM_MSTEP_NRAW
-#define GMM_MSTEP_NRAW 4
-#endif
-#ifndef GMM_MSTEP_TRIM
-#define GMM_MSTEP_TRIM 0
-#endif
-// Operand split of the M-step (build-time knobs, defaults = the shipped configuration):
-//   GMM_MSTEP_RN = 1  hi = round-to-nearest FP16 of the value, lo = FP16(value - hi): the dropped lo*lo product is then
-//                     zero-mean.  With the truncating split (0: hi = leading 11 bits) hi <= |value| always, lo*lo has one
-//                     sign and the three kept products carry a systematic relative bias of ~1e-7 that is different for
-//                     the count row (phi = 1: none), the first and the second moments — the raw-moment cancellation
-//                     (|mu - shift|^2 / sigma^2 ~ 100) turns it into ~1e-5 on covariance entries (scripts/emu_mstep.py).
-//   GMM_MSTEP_P4 = 1  also issue the fourth product (phi_lo, g_lo) — diagnostic only.
-#ifndef GMM_MSTEP_RN
-#define GMM_MSTEP_RN 1
-#endif
-#ifndef GMM_MSTEP_P4
-#define GMM_MSTEP_P4 0
-#endif
-constexpr int kNST = GMM_MSTEP_NST;      // operand stages
-constexpr int kNRAW = GMM_MSTEP_NRAW;    // raw (TMA) stages
-constexpr int kChunkSub = GMM_CHUNKSUB;     // sub-tiles between TMEM flushes
+constexpr int kNCL = 64;         // clusters per CTA pass
+constexpr int kNST = 3;          // operand stages
+constexpr int kNRAW = 4;         // raw (TMA) stages
+constexpr int kChunkSub = 4;     // sub-tiles per accumulation chain: 128 events (the exactness budget above)
 constexpr int kMThreads = 512;
-constexpr float kGammaScale = 1024.0f;   // responsibilities are scaled by 2^10 before the FP16 split
+constexpr int kPhiBits = 9;      // |ph| <= 2^9 quanta
+constexpr float kGammaScale = 1024.0f;               // responsibilities are scaled by 2^10 in the operand
+constexpr float kGammaMagic = 1.5f * 33554432.0f;    // 1.5 * 2^25: ulp = 4 = 2^-8 in the scaled units
 
 template <int D> struct MCfg {
     static constexpr int F = 1 + D + D * (D + 1) / 2;
     static constexpr int NCHUNK = (F + 7) / 8;            // 16-byte feature chunks actually written
     static constexpr int MT = (F + 127) / 128;            // M tiles of 128 feature rows
-    // bytes of one precision part (hi or lo).  Trimmed: only the NCHUNK real 8-row groups; the last M tile's descriptor then
-    // reads past the part into whatever follows (finite FP16 data of the next part / stage / the responsibility images):
-    // garbage only in output rows >= 8 * NCHUNK, which nobody reads.
-    static constexpr int PHI_PART = GMM_MSTEP_TRIM ? NCHUNK * 8 * kTE * 2 : MT * 128 * kTE * 2;
+    static constexpr int PHI_PART = MT * 128 * kTE * 2;   // bytes of one part (leading or remainder)
     static constexpr int PHI_STAGE = 2 * PHI_PART;
     static constexpr int G_PART = kNCL * kTE * 2;
-    static constexpr int G_STAGE = 2 * G_PART;
+    static constexpr int G_STAGE = 2 * G_PART;            // [gh (64 rows) ; gl (64 rows)] = ONE K-major N = 128 image
     static constexpr int RAWX = D * kTE * 4;              // [D][32 events] from the SoA copy
     static constexpr int RAWG = kNCL * kTE * 4;
     static constexpr int OFF_PHI = 0;
@@ -116,9 +101,14 @@ template <int D> struct MCfg {
     static constexpr int OFF_RAWG = OFF_RAWX + kNRAW * RAWX;
     static constexpr int OFF_BAR = OFF_RAWG + kNRAW * RAWG;
     static constexpr int SMEM_BYTES = OFF_BAR + 512;
-    static constexpr int TMEM_COLS = 2 * MT * kNCL;       // two accumulator buffers
+    static constexpr int TMEM_COLS = MT * 128;            // per feature tile: [ph gh | ph gl + pl gh]
     static_assert(OFF_RAWG % 1024 == 0 && RAWG % 1024 == 0, "SWIZZLE_128B TMA destinations need 1024-byte alignment");
+    static_assert(MT <= 3, "accumulator tiles");
 };
+
+// Rounding constants of the feature rows (kernel parameter: read as constant-bank operands, the row index is
+// static after unrolling): magic[f] = 1.5 * 2^23 * q_f, so that (v + magic) - magic = q_f * round(v / q_f).
+template <int D> struct MMagic { float m[MCfg<D>::NCHUNK * 8]; };
 
 __host__ __device__ constexpr int tri_row(int t) {        // t = i(i+1)/2 + j, j <= i  ->  i
     int i = 0;
@@ -132,66 +122,54 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 
-// FP16 hi/lo split of a pair of values, packed as half2 bits (low half = first value).
-__device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-#if GMM_MSTEP_RN
-    const __half2 h = __floats2half2_rn(v0, v1);
-    const float2 f = __half22float2(h);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    lo = pack_half2(v0 - f.x, v1 - f.y);                                   // exact remainders, rounded once
-#else
-    const float h0 = __uint_as_float(__float_as_uint(v0) & 0xFFFFE000u);   // top 11 significant bits: exact in FP16
-    const float h1 = __uint_as_float(__float_as_uint(v1) & 0xFFFFE000u);
-    hi = pack_half2(h0, h1);
-    lo = pack_half2(v0 - h0, v1 - h1);
-#endif
-}
-
-// value of feature f for centred/scaled event z (f is a compile-time constant after unrolling)
+// Leading part / remainder of feature f of the centred/scaled event z (f is a compile-time constant after
+// unrolling).  Second moments: both parts come from the EXACT product (fused multiply-adds), rounded once each.
 template <int D>
-__device__ __forceinline__ float feature_value(const float (&z)[D], int f) {
+__device__ __forceinline__ void feature_split(const float (&z)[D], int f, float magic, float& h, float& l) {
     constexpr int F = MCfg<D>::F;
-    if (f == 0) return 1.0f;
-    if (f <= D) return z[f - 1];
-    if (f < F) {
+    if (f == 0) { h = 1.0f; l = 0.0f; }
+    else if (f <= D) {
+        const float v = z[f - 1];
+        h = __fsub_rn(__fadd_rn(v, magic), magic);
+        l = __fsub_rn(v, h);
+    } else if (f < F) {
         const int t = f - 1 - D;
         const int i = tri_row(t);
         const int j = t - i * (i + 1) / 2;
-        return z[i] * z[j];
-    }
-    return 0.0f;
+        h = __fsub_rn(__fmaf_rn(z[i], z[j], magic), magic);
+        l = __fmaf_rn(z[i], z[j], -h);
+    } else { h = 0.0f; l = 0.0f; }
 }
 
 // Builds the 16-byte chunks c = P, P+4, P+8, ... of the feature vector of one event and
-// stores hi/lo parts into the MN-major operand image:
+// stores both parts into the MN-major operand image:
 //   byte(f, e) = (f/8)*512 + (e/8)*128 + (e%8)*16 + (f%8)*2        (LBO = 128, SBO = 512)
 template <int D, int P>
-__device__ __forceinline__ void build_phi_chunks(const float (&z)[D], uint8_t* hi_base, uint8_t* lo_base, int e) {
+__device__ __forceinline__ void build_phi_chunks(const float (&z)[D], const MMagic<D>& mg, uint8_t* hi_base, uint8_t* lo_base, int e) {
     constexpr int NCHUNK = MCfg<D>::NCHUNK;
     const int eoff = (e >> 3) * 128 + (e & 7) * 16;
 #pragma unroll
     for (int c = P; c < NCHUNK; c += 4) {
+        float hi[8], lo[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) feature_split<D>(z, c * 8 + u, mg.m[c * 8 + u], hi[u], lo[u]);
         uint4 h, l;
-        split_pair(feature_value<D>(z, c * 8 + 0), feature_value<D>(z, c * 8 + 1), h.x, l.x);
-        split_pair(feature_value<D>(z, c * 8 + 2), feature_value<D>(z, c * 8 + 3), h.y, l.y);
-        split_pair(feature_value<D>(z, c * 8 + 4), feature_value<D>(z, c * 8 + 5), h.z, l.z);
-        split_pair(feature_value<D>(z, c * 8 + 6), feature_value<D>(z, c * 8 + 7), h.w, l.w);
+        h.x = pack_half2(hi[0], hi[1]); h.y = pack_half2(hi[2], hi[3]); h.z = pack_half2(hi[4], hi[5]); h.w = pack_half2(hi[6], hi[7]);   // exact: <= 10 bits
+        l.x = pack_half2(lo[0], lo[1]); l.y = pack_half2(lo[2], lo[3]); l.z = pack_half2(lo[4], lo[5]); l.w = pack_half2(lo[6], lo[7]);
         *reinterpret_cast<uint4*>(hi_base + c * 512 + eoff) = h;
         *reinterpret_cast<uint4*>(lo_base + c * 512 + eoff) = l;
     }
 }
 
-// GS: responsibilities enter the MMA as an FP16 hi/lo pair (three products per element).  With GS = false
-// they are rounded once to FP16 (round to nearest, after the 2^10 scaling) and only (phi_hi, g) + (phi_lo, g)
-// are issued: a third less tensor and shared-memory work (measured: -10 % kernel time at N=10M, D=24, K=64).  The rounding perturbs every weight by an unbiased
-// relative error <= 2^-12, consistently in N_k, the first and the second moments, so the result is the exact
-// M-step of weights g(1 + d): the perturbation averages over the events of a cluster (~1e-4 / sqrt(n_eff))
-// and is not amplified by the centring cancellation.  Measured per-call deviation of the means on clusters
-// of ~10 events: 2e-4 without the pair against 5e-6 with it, so the pair is the default.
-template <int D, bool GS>
+// Feature tile `mt` is drained after sub-tile i when its 128-event chain ends there: the chains of the tiles are
+// staggered by one sub-tile each, so that only one tile is being drained at a time (single-buffered accumulators).
+__device__ __forceinline__ bool chain_ends(int i, int mt, int nsub) { return ((i + mt) % kChunkSub) == kChunkSub - 1 || i == nsub - 1; }
+__device__ __forceinline__ bool chain_starts(int i, int mt) { return i == 0 || ((i + mt) % kChunkSub) == 0; }
+
+template <int D>
 __global__ void __launch_bounds__(kMThreads, 1)
 mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g, int n,
-                double* __restrict__ scratch, int events_per_cta) {
+                float* __restrict__ scratch, int events_per_cta, const __grid_constant__ MMagic<D> magic) {
     using C = MCfg<D>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -199,9 +177,9 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     uint64_t* raw_empty = bars + kNRAW;        // [kNRAW]
     uint64_t* op_full = bars + 2 * kNRAW;      // [kNST]
     uint64_t* op_empty = op_full + kNST;       // [kNST]
-    uint64_t* acc_full = op_empty + kNST;      // [2]
-    uint64_t* acc_empty = acc_full + 2;        // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* acc_full = op_empty + kNST;      // [MT]  chain of feature tile mt complete (tcgen05.commit)
+    uint64_t* acc_empty = acc_full + 3;        // [MT]  tile mt drained (4 flush warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 3);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int e_begin = blockIdx.x * events_per_cta;
@@ -214,7 +192,7 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     if (threadIdx.x == 0) {
         for (int s = 0; s < kNRAW; s++) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
         for (int s = 0; s < kNST; s++) { mbar_init(&op_full[s], 4); mbar_init(&op_empty[s], 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        for (int s = 0; s < 3; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -243,33 +221,36 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_f16(128, kNCL, /*A MN-major*/ true, /*B MN-major*/ false);
+            constexpr uint32_t idesc128 = make_idesc_f16(128, 2 * kNCL, /*A MN-major*/ true, /*B MN-major*/ false);
+            constexpr uint32_t idesc64 = make_idesc_f16(128, kNCL, true, false);
+            uint32_t drained = 0;                              // bit mt: wait parity of acc_empty[mt]
+            uint32_t used = 0;                                 // bit mt: tile mt has completed at least one chain
             for (int i = 0; i < nsub; i++) {
                 const int os = i % kNST, oph = (i / kNST) & 1;
-                const int chunk = i / kChunkSub, ab = chunk & 1;
-                const bool first = (i % kChunkSub) == 0;
-                if (first) mbar_wait_parked(&acc_empty[ab], ((chunk >> 1) & 1) ^ 1, 100);
                 mbar_wait_parked(&op_full[os], oph, 100);
                 tc_fence_after();
                 const uint32_t phi = smem_u32(smem + C::OFF_PHI + os * C::PHI_STAGE);
                 const uint32_t gam = smem_u32(smem + C::OFF_G + os * C::G_STAGE);
-                const uint32_t dcol = tmem + ab * (C::MT * kNCL);
 #pragma unroll
-                for (int seg = 0; seg < (GS ? 3 + GMM_MSTEP_P4 : 2); seg++) {   // (phi_hi, g_hi), (phi_lo, g_hi), (phi_hi, g_lo) [, (phi_lo, g_lo)]
-                    const uint32_t pa = phi + ((seg & 1) ? C::PHI_PART : 0);
-                    const uint32_t pb = gam + (seg >= 2 ? C::G_PART : 0);
+                for (int mt = 0; mt < C::MT; mt++) {
+                    const bool first = chain_starts(i, mt);
+                    if (first && ((used >> mt) & 1u)) {        // the previous chain of this tile must have been drained
+                        mbar_wait_parked(&acc_empty[mt], (drained >> mt) & 1u, 100);
+                        drained ^= 1u << mt;
+                        tc_fence_after();
+                    }
+                    const uint32_t dcol = tmem + mt * 128;
 #pragma unroll
                     for (int ks = 0; ks < kTE / 16; ks++) {
-                        const uint64_t bdesc = make_smem_desc(pb + ks * 256, /*LBO*/ 128, /*SBO*/ 512);
-#pragma unroll
-                        for (int mt = 0; mt < C::MT; mt++) {
-                            const uint64_t adesc = make_smem_desc(pa + mt * 8192 + ks * 256, /*LBO*/ 128, /*SBO*/ 512);
-                            mma_f16_ss(dcol + mt * kNCL, adesc, bdesc, idesc, !(first && seg == 0 && ks == 0));
-                        }
+                        const uint64_t bdesc = make_smem_desc(gam + ks * 256, /*LBO*/ 128, /*SBO*/ 512);     // rows 0-63 gh, 64-127 gl
+                        const uint64_t ah = make_smem_desc(phi + mt * 8192 + ks * 256, /*LBO*/ 128, /*SBO*/ 512);
+                        const uint64_t al = make_smem_desc(phi + C::PHI_PART + mt * 8192 + ks * 256, 128, 512);
+                        mma_f16_ss(dcol, ah, bdesc, idesc128, !(first && ks == 0));     // [ph gh | ph gl]
+                        mma_f16_ss(dcol + kNCL, al, bdesc, idesc64, true);             //          += pl gh
                     }
+                    if (chain_ends(i, mt, nsub)) { mma_commit(&acc_full[mt]); used |= 1u << mt; }
                 }
                 mma_commit(&op_empty[os]);                    // operand stage reusable once these MMAs retire
-                if ((i % kChunkSub) == kChunkSub - 1 || i == nsub - 1) mma_commit(&acc_full[ab]);
             }
         }
       }
@@ -307,50 +288,47 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 const uint8_t* grow = smem + C::OFF_RAWG + rs * C::RAWG + k * (kTE * 4);
                 const float4 a = *reinterpret_cast<const float4*>(grow + (((2 * ce) ^ (k & 7)) << 4));
                 const float4 b = *reinterpret_cast<const float4*>(grow + (((2 * ce + 1) ^ (k & 7)) << 4));
-                float g[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                const float g[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
                 gdep += a.x + b.x;
-                if (GS) {
+                float hi[8], lo[8];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) g[u] *= kGammaScale;
-                    split_pair(g[0], g[1], gh[it2].x, gl[it2].x);
-                    split_pair(g[2], g[3], gh[it2].y, gl[it2].y);
-                    split_pair(g[4], g[5], gh[it2].z, gl[it2].z);
-                    split_pair(g[6], g[7], gh[it2].w, gl[it2].w);
-                } else {
-#pragma unroll
-                    for (int u = 0; u < 8; u++) g[u] *= kGammaScale;
-                    gh[it2] = make_uint4(pack_half2(g[0], g[1]), pack_half2(g[2], g[3]), pack_half2(g[4], g[5]), pack_half2(g[6], g[7]));
+                for (int u = 0; u < 8; u++) {                  // gh = 4 * round(256 g) (0 .. 1024), gl = 1024 g - gh, both from the exact product
+                    hi[u] = __fsub_rn(__fmaf_rn(g[u], kGammaScale, kGammaMagic), kGammaMagic);
+                    lo[u] = __fmaf_rn(g[u], kGammaScale, -hi[u]);
                 }
+                gh[it2] = make_uint4(pack_half2(hi[0], hi[1]), pack_half2(hi[2], hi[3]), pack_half2(hi[4], hi[5]), pack_half2(hi[6], hi[7]));
+                gl[it2] = make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]), pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7]));
             }
             // The raw tiles must BE in registers before the stage goes back to the TMA producer: an mbarrier arrive does
-            // not wait for the warp's outstanding LDS (measured: with nothing consuming the z loads before the arrive, the
-            // refill of the stage overtook the loads of the last dimensions).  The arrive is therefore made data-dependent
-            // on every load of this thread: one FADD chain over z and one component of each responsibility vector; the
-            // compared bit pattern (a signalling NaN) is never the result of an addition, whatever the data.
+            // not wait for the warp's outstanding LDS (measured in round 1: with nothing consuming the z loads before the
+            // arrive, the refill of the stage overtook the loads of the last dimensions).  The arrive is therefore made
+            // data-dependent on every load of this thread: a sum over z and one component of each responsibility vector,
+            // folded into the arrive's own operand list below (the asm statement consumes the value, so neither the
+            // compiler nor the hardware can retire it before the loads have landed).
             float dep = gdep;
 #pragma unroll
             for (int d = 0; d < D; d++) dep += z[d];
-            const bool never = __float_as_uint(dep) == 0xff800001u;
             __syncwarp();
-            if (lane == 0 || never) mbar_arrive(&raw_empty[rs]);
+            if (lane == 0) mbar_arrive_after(&raw_empty[rs], dep);
+            else asm volatile("" ::"f"(dep));
             mbar_wait_parked(&op_empty[os], oph ^ 1, 200);
             uint8_t* phi_hi = smem + C::OFF_PHI + os * C::PHI_STAGE;
             uint8_t* phi_lo = phi_hi + C::PHI_PART;
             switch (part) {
-                case 0: build_phi_chunks<D, 0>(z, phi_hi, phi_lo, lane); break;
-                case 1: build_phi_chunks<D, 1>(z, phi_hi, phi_lo, lane); break;
-                case 2: build_phi_chunks<D, 2>(z, phi_hi, phi_lo, lane); break;
-                default: build_phi_chunks<D, 3>(z, phi_hi, phi_lo, lane); break;
+                case 0: build_phi_chunks<D, 0>(z, magic, phi_hi, phi_lo, lane); break;
+                case 1: build_phi_chunks<D, 1>(z, magic, phi_hi, phi_lo, lane); break;
+                case 2: build_phi_chunks<D, 2>(z, magic, phi_hi, phi_lo, lane); break;
+                default: build_phi_chunks<D, 3>(z, magic, phi_hi, phi_lo, lane); break;
             }
             {
-                // K-major B image: byte(k, e) = (k/8)*512 + (e/8)*128 + (k%8)*16 + (e%8)*2      (LBO = 128, SBO = 512)
+                // K-major B image: byte(k, e) = (k/8)*512 + (e/8)*128 + (k%8)*16 + (e%8)*2      (LBO = 128, SBO = 512); gl = rows 64..127
                 uint8_t* g_hi = smem + C::OFF_G + os * C::G_STAGE;
 #pragma unroll
                 for (int it2 = 0; it2 < 2; it2++) {
                     const int item = bt + it2 * 128;
                     const int kg = item >> 5, l = item & 31;
                     *reinterpret_cast<uint4*>(g_hi + kg * 512 + l * 16) = gh[it2];
-                    if (GS) *reinterpret_cast<uint4*>(g_hi + C::G_PART + kg * 512 + l * 16) = gl[it2];
+                    *reinterpret_cast<uint4*>(g_hi + C::G_PART + kg * 512 + l * 16) = gl[it2];
                 }
             }
             fence_proxy_async_smem();
@@ -361,44 +339,41 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
         // ===================== flush: TMEM -> register-resident FP32 partial sums =====================
         const int q = warp - 12;                                   // TMEM lane quadrant (= warp % 4)
-        const int nchunks = (nsub + kChunkSub - 1) / kChunkSub;
         float racc[C::MT * kNCL];
 #pragma unroll
         for (int j = 0; j < C::MT * kNCL; j++) racc[j] = 0.0f;
-        // second level: every kSpill chunks the FP32 partial sums move into this thread's double
-        // partials in the (L2-resident) per-CTA scratch, bounding the FP32 random walk to kSpill adds
-        constexpr int kSpill = GMM_SPILL;
-        double* my = scratch + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * C::MT * 128 + q * 32 + lane) * kNCL;
-        for (int c = 0; c < nchunks; c++) {
-            const int ab = c & 1;
-            mbar_wait_parked(&acc_full[ab], (c >> 1) & 1, 500);
-            tc_fence_after();
+        uint32_t full = 0;                                         // bit mt: wait parity of acc_full[mt]
+        for (int i = 0; i < nsub; i++) {
 #pragma unroll
             for (int mt = 0; mt < C::MT; mt++) {
+                if (!chain_ends(i, mt, nsub)) continue;
+                mbar_wait_parked(&acc_full[mt], (full >> mt) & 1u, 300);
+                full ^= 1u << mt;
+                tc_fence_after();
+                const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + mt * 128;
 #pragma unroll
-                for (int h = 0; h < kNCL / 32; h++) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + ab * (C::MT * kNCL) + mt * kNCL + h * 32, r);
+                for (int b = 0; b < kNCL / 16; b++) {
+                    uint32_t a1[16], a2[16];
+                    tmem_ld_32x16(tbase + b * 16, a1);                 // exact leading products
+                    tmem_ld_32x16(tbase + kNCL + b * 16, a2);          // remainder products
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; j++) racc[(mt * 2 + h) * 32 + j] += __uint_as_float(r[j]);
+                    for (int j = 0; j < 16; j++)
+                        racc[mt * kNCL + b * 16 + j] += __uint_as_float(a1[j]) + __uint_as_float(a2[j]);
                 }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[ab]);
-            if ((c % kSpill) == kSpill - 1 || c == nchunks - 1) {
-                // fire-and-forget double reductions (RED.ADD.F64) into this thread's private slots of the
-                // zero-initialised scratch: no load latency on the flush path
-#pragma unroll
-                for (int mt = 0; mt < C::MT; mt++)
-#pragma unroll
-                    for (int j = 0; j < kNCL; j++) {
-                        atomicAdd(my + (size_t)mt * 128 * kNCL + j, (double)racc[mt * kNCL + j]);
-                        racc[mt * kNCL + j] = 0.0f;
-                    }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[mt]);
             }
         }
+        // one plain store of this thread's partial sums: [cta][tile][row][64 clusters]
+        float* my = scratch + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * C::MT * 128 + q * 32 + lane) * kNCL;
+#pragma unroll
+        for (int mt = 0; mt < C::MT; mt++)
+#pragma unroll
+            for (int j = 0; j < kNCL; j += 4)
+                *reinterpret_cast<float4*>(my + (size_t)mt * 128 * kNCL + j) =
+                    make_float4(racc[mt * kNCL + j], racc[mt * kNCL + j + 1], racc[mt * kNCL + j + 2], racc[mt * kNCL + j + 3]);
     }
     tc_fence_before();
     __syncthreads();
@@ -420,9 +395,9 @@ __global__ void standardise_soa_kernel(const float* __restrict__ xs, float* __re
 
 // Reduce the per-CTA FP32 partials in double, undo the operand scaling and write the packed statistics.
 __global__ void __launch_bounds__(256)
-mstep_tc_finalize_kernel(const double* __restrict__ scratch, int ncta_x, int MT, int K, int D, int F,
+mstep_tc_finalize_kernel(const float* __restrict__ scratch, int ncta_x, int MT, int K, int D, int F,
                          const double* __restrict__ scale, double* __restrict__ stats) {
-    // one block per feature row f; thread -> (cluster column, quarter of the CTAs): 512-byte coalesced reads
+    // one block per feature row f; thread -> (cluster column, quarter of the CTAs): 256-byte coalesced reads
     __shared__ double part[4][kNCL];
     const int f = blockIdx.x, mt = f / 128, row = f % 128;
     const int col = threadIdx.x & (kNCL - 1), q = threadIdx.x / kNCL;
@@ -436,7 +411,7 @@ mstep_tc_finalize_kernel(const double* __restrict__ scratch, int ncta_x, int MT,
     for (int ty = 0; ty * kNCL < K; ty++) {
         double s = 0;
         for (int cx = q; cx < ncta_x; cx += 4)
-            s += scratch[(((size_t)(ty * ncta_x + cx) * MT + mt) * 128 + row) * kNCL + col];
+            s += (double)scratch[(((size_t)(ty * ncta_x + cx) * MT + mt) * 128 + row) * kNCL + col];
         part[q][col] = s;
         __syncthreads();
         const int k = ty * kNCL + col;
@@ -474,7 +449,6 @@ mstep_tc_finalize_kernel(const double* __restrict__ scratch, int ncta_x, int MT,
 //               max / sum-exp2 (+ exchange between the warpgroups) -> responsibilities
 //               (coalesced 128-byte row segments) + log-likelihood (double)
 // ===========================================================================
-constexpr int kEThreads = 512;
 
 // GMM_ESTEP_PROF=1 (build-time, diagnostic variant only): the epilogue of CTA 0 / warp 8 accumulates clock64() spans of its
 // phases and prints them at the end of the kernel — where do the cycles of a tile go (waiting for accumulators, tcgen05.ld,
@@ -492,7 +466,8 @@ constexpr int kEThreads = 512;
 // ("block" c) only need the K chunks z_j with j >= c.  Columns are therefore grouped by block:
 // one MMA N tile = block c of 16 clusters (N = 128), and block c issues only the k-steps it needs —
 // 5 + 4 + 2 = 11 instead of 15 at D = 24 (-27 % tensor work and TMEM accumulator traffic).
-template <int D, int NWG = 2> struct ECfg {
+template <int D> struct ECfg {
+    static constexpr int NWG = 2;                             // epilogue warpgroups
     static_assert(D % 8 == 0, "tensor E-step: D must be a multiple of 8");
     static constexpr int CP = D / 8;                          // 8-wide chunks of z / blocks of output columns
     static constexpr int NLO = (CP + 1 + 1) / 2 * 2;          // chunks of the [zh | ones (| pad)] x [Wl | v] part
@@ -503,7 +478,7 @@ template <int D, int NWG = 2> struct ECfg {
     static constexpr int MAXSG = 64 / GB;                     // up to 64 clusters resident
     static constexpr int NBUF = 512 / N;                      // TMEM accumulator buffers (4)
     static constexpr int CW = GB / NWG;                       // clusters per epilogue warpgroup per supergroup
-    static constexpr int LPT = MAXSG * CW;                    // logits held per epilogue thread (32, or 16 with 4 warpgroups)
+    static constexpr int LPT = MAXSG * CW;                    // logits held per epilogue thread (32)
     static constexpr int A_STAGE = NCHKA * 128 * 16;
     static constexpr int B_BLOCK = NCHKB * N * 16;            // one block of one supergroup
     static constexpr int B_SG = CP * B_BLOCK;
@@ -514,26 +489,21 @@ template <int D, int NWG = 2> struct ECfg {
     static constexpr int OFF_BAR = OFF_EX + 2 * NWG * 128 * 8;
     static constexpr int SMEM_BYTES = OFF_BAR + 512;
     static constexpr int THREADS = 256 + 128 * NWG;           // warpgroup 0, converters, NWG epilogue warpgroups
-    static_assert(NWG == 2 || NWG == 4, "epilogue warpgroups");
 };
 
-// ALT = false: both epilogue warpgroups work on every tile (each takes 8 of the 16 clusters of a supergroup and they
-// exchange (max, sum) through shared memory).  ALT = true (experimental, GMM_ESTEP_ALT=1): the warpgroups take alternate
-// tiles and each handles all 16 clusters — no exchange, and the log-sum-exp / store phase of one tile overlaps the
-// accumulator reads of the next, so the MMA issuer is not held up by full TMEM buffers during that phase.
-// NWG = 4 (experimental, GMM_ESTEP_WG4=1): four epilogue warpgroups, each with 4 of the 16 clusters of a supergroup (one
-// tcgen05.ld.x32 per block and warp, 16 logits per thread, 96 registers) — four instead of two epilogue warps per sub-core
-// to hide the load / mbarrier / MUFU latencies the two-warp version exposes (tc_probe T6: the hardware floor is the MMA time).
-template <int D, bool ALT, int NWG = 2>
-__global__ void __launch_bounds__(256 + 128 * NWG, 1)
+// Both epilogue warpgroups work on every tile: each takes 8 of the 16 clusters of a supergroup and they exchange
+// (max, sum) through shared memory.  (Round 1 also carried an alternate-tile variant and a four-warpgroup variant;
+// both were measured — 1.73 ms and 1.85 ms per 4M events x 2.5 against 1.67 — and removed.)
+template <int D>
+__global__ void __launch_bounds__(512, 1)
 estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_img, const float* __restrict__ ck,
                 const float* __restrict__ shift_f, const float* __restrict__ inv_scale_f, float* __restrict__ memb,
                 size_t pitch, int n, int K, int NSG, double* __restrict__ ll_out, float* __restrict__ den_out) {
     // K / NSG / b_img / ck / memb describe ONE pass of at most 64 clusters.  With more than 64 clusters the host
     // launches one pass per 64 (den_out != nullptr): each pass normalises within itself and records its
     // log-denominator per event; estep_tc_combine_kernel then rescales the passes against each other.
-    using C = ECfg<D, NWG>;
-    static_assert(!ALT || NWG == 2, "alternate-tile epilogue is written for two warpgroups");
+    using C = ECfg<D>;
+    constexpr int NWG = C::NWG;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
     uint64_t* a_full = bars;            // [2]  4 converter warps
@@ -542,9 +512,6 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
     uint64_t* acc_full = bars + 5;      // [NBUF]  tcgen05.commit
     uint64_t* acc_empty = bars + 5 + C::NBUF;     // [NBUF]  8 epilogue warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * C::NBUF);
-    // ALT: the odd tiles' accumulators are announced on a second set of barriers, so that each epilogue warpgroup only
-    // ever waits for the NEXT phase of a barrier (a parity wait cannot tell phase p from phase p + 2)
-    uint64_t* acc_full_odd = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR + 384);   // [NBUF]
     float2* ck_s = reinterpret_cast<float2*>(smem + C::OFF_CK);
     float2* ex = reinterpret_cast<float2*>(smem + C::OFF_EX);
     float* sh_s = reinterpret_cast<float*>(smem + C::OFF_BAR + 128);   // [32] shift, [32] inverse scale
@@ -556,9 +523,8 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; s++) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < C::NBUF; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], ALT ? 4 : 4 * NWG); }
+        for (int s = 0; s < C::NBUF; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4 * NWG); }
         mbar_init(b_full, 1);
-        if (ALT) for (int s = 0; s < C::NBUF; s++) mbar_init(&acc_full_odd[s], 1);
         fence_mbar_init();
     }
     // base-2 logits in the epilogue: l2 = ck * log2(e) + (-0.5 * log2(e) / scale_k^2) * |scale_k * y|^2   (the per-cluster
@@ -579,10 +545,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
 
     // register re-partition inside the CTA's launch allocation (512 x 128): WG0 40, converters 72, epilogue 2 x 200
     if (warp < 4) {
-      // register pools: NWG = 2 launches 512 x 128, NWG = 4 launches 768 x 80 (= 61440): 128 x (24 + 64) + 512 x 96 = 60416
-      if constexpr (NWG == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-      else if constexpr (ALT) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-      else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
       if (warp == 1) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
@@ -618,7 +581,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                                 acc = true;
                             }
                         }
-                        mma_commit(ALT && (it & 1) ? &acc_full_odd[buf] : &acc_full[buf]);
+                        mma_commit(&acc_full[buf]);
                         buf = (buf + 1) % C::NBUF;
                     }
                 }
@@ -627,9 +590,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
         }
       }
     } else if (warp < 8) {
-        if constexpr (NWG == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        else if constexpr (ALT) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        else asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
         // ===================== converters =====================
         const int row = threadIdx.x - 128;
         for (int it = 0; it < my_tiles; it++) {
@@ -675,106 +636,8 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
             if (lane == 0) mbar_arrive(&a_full[st]);
         }
     } else {
-        if constexpr (NWG == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
-        else if constexpr (ALT) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");   // 128 x (32 + 64 + 2 x 208) = 64K registers
-        else asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
         // ===================== epilogue =====================
-      if constexpr (ALT) {
-        // warpgroup g takes the tiles it = g, g+2, ...; thread = event row, all clusters of the pass in this thread
-        const int g = (warp - 8) >> 2, q = warp & 3;
-        const int row = q * 32 + lane;
-        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        const int NB = NSG * C::CP;                            // blocks per tile; buffer of block j: j % NBUF (restarts per tile)
-        constexpr float kLn2 = 0.6931471805599453f;
-        double ll_acc = 0.0;
-        for (int it = g; it < my_tiles; it += 2) {
-            const long long e = (long long)((int)blockIdx.x + it * (int)gridDim.x) * 128 + row;
-            uint32_t pf[C::NBUF];                              // parity of acc_full[b] at its first use in this tile
-#pragma unroll
-            for (int b = 0; b < C::NBUF; b++) {
-                const int uses = b < NB ? (NB - b + C::NBUF - 1) / C::NBUF : 0;   // uses of buffer b per tile
-                pf[b] = (uint32_t)((it >> 1) * uses) & 1u;     // this warpgroup's own barrier set: its (it / 2)-th tile
-            }
-            float lg[C::MAXSG * C::GB];                        // base-2 logits of all clusters of the pass
-            float mx = -INFINITY;
-#pragma unroll
-            for (int sg = 0; sg < C::MAXSG; sg++) {
-                if (sg < NSG) {
-                    uint64_t qs[C::GB];                        // packed partial sums of squares, one pair per cluster
-#pragma unroll
-                    for (int i = 0; i < C::GB; i++) qs[i] = 0ull;
-#pragma unroll
-                    for (int c = 0; c < C::CP; c++) {
-                        const int buf = (sg * C::CP + c) % C::NBUF;
-                        mbar_wait_parked(g ? &acc_full_odd[buf] : &acc_full[buf], pf[buf], 200);
-                        pf[buf] ^= 1u;
-                        tc_fence_after();
-#pragma unroll
-                        for (int half = 0; half < 2; half++) {
-                            const uint32_t tcol = tmem + lane_base + buf * C::N + half * 64;
-                            uint32_t v[64];                    // 8 clusters x 8 columns
-                            tmem_ld_32x32(tcol, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-                            tmem_ld_32x32(tcol + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-                            tmem_ld_wait();
-                            if (half == 1) {                   // the whole block is in registers: hand the buffer back
-                                tc_fence_before();
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive(&acc_empty[buf]);
-                            }
-#pragma unroll
-                            for (int i = 0; i < 8; i++) {
-                                sq_acc2(qs[half * 8 + i], v[i * 8 + 0], v[i * 8 + 1]);
-                                sq_acc2(qs[half * 8 + i], v[i * 8 + 2], v[i * 8 + 3]);
-                                sq_acc2(qs[half * 8 + i], v[i * 8 + 4], v[i * 8 + 5]);
-                                sq_acc2(qs[half * 8 + i], v[i * 8 + 6], v[i * 8 + 7]);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < C::GB; i++) {
-                        float lo, hi;
-                        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(qs[i]));
-                        const float2 cm = ck_s[sg * C::GB + i];
-                        const float l = fmaf(cm.y, lo + hi, cm.x);
-                        lg[sg * C::GB + i] = l;
-                        mx = fmaxf(mx, l);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < C::GB; i++) lg[sg * C::GB + i] = -INFINITY;
-                }
-            }
-            float sm = 0.f;                                    // estep2, gaussian_kernel.cu:481-503
-#pragma unroll
-            for (int j = 0; j < C::MAXSG * C::GB; j++) { lg[j] = ex2_approx(lg[j] - mx); sm += lg[j]; }
-            const float denom = fmaf(mx, kLn2, logf(sm));
-            const float scale = 1.0f / sm;
-            if (e < n) {
-                if (den_out) den_out[e] = denom;
-                else ll_acc += (double)denom;
-                float* gp = memb + e;
-#pragma unroll
-                for (int kg = 0; kg < C::MAXSG * C::GB / 8; kg++) {          // whole 8-cluster groups (rows padded to 8)
-                    if (kg * 8 < K) {
-                        float* gq = gp + (size_t)(kg * 8) * pitch;
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            *gq = lg[kg * 8 + i] * scale;                    // :498-501
-                            gq += pitch;
-                        }
-                    }
-                }
-            }
-        }
-        if (den_out == nullptr) {
-            ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 16);
-            ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 8);
-            ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 4);
-            ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 2);
-            ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 1);
-            if (lane == 0) atomicAdd(ll_out, ll_acc);
-        }
-      } else {
         const int wg = (warp - 8) >> 2, q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
@@ -805,7 +668,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                         const uint32_t tcol = tmem + lane_base + buf * C::N + wg * (C::CW * 8);
                         uint32_t v[C::CW * 8];                 // CW clusters x 8 columns
                         tmem_ld_32x32(tcol, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-                        if constexpr (C::CW * 8 > 32) tmem_ld_32x32(tcol + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[C::CW * 8 - 32]));
+                        tmem_ld_32x32(tcol + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
                         tmem_ld_wait();
                         EPROF(const long long p2 = clock64(); pr_ld += p2 - p1;)
                         tc_fence_before();
@@ -813,18 +676,10 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                         if (lane == 0) mbar_arrive(&acc_empty[buf]);   // the block is in registers: hand the buffer back
 #pragma unroll
                         for (int i = 0; i < C::CW; i++) {
-                            if constexpr (NWG == 2) {
-                                sq_acc2(qa[i], v[i * 8 + 0], v[i * 8 + 1]);
-                                sq_acc2(qb[i], v[i * 8 + 2], v[i * 8 + 3]);
-                                sq_acc2(qa[i], v[i * 8 + 4], v[i * 8 + 5]);
-                                sq_acc2(qb[i], v[i * 8 + 6], v[i * 8 + 7]);
-                            } else {                           // 96-register budget: one accumulator pair per cluster
-                                sq_acc2(qa[i], v[i * 8 + 0], v[i * 8 + 1]);
-                                sq_acc2(qa[i], v[i * 8 + 2], v[i * 8 + 3]);
-                                sq_acc2(qa[i], v[i * 8 + 4], v[i * 8 + 5]);
-                                sq_acc2(qa[i], v[i * 8 + 6], v[i * 8 + 7]);
-                                asm volatile("" : "+l"(qa[i]));   // keep this block's squares ahead of the next block's load (register budget)
-                            }
+                            sq_acc2(qa[i], v[i * 8 + 0], v[i * 8 + 1]);
+                            sq_acc2(qb[i], v[i * 8 + 2], v[i * 8 + 3]);
+                            sq_acc2(qa[i], v[i * 8 + 4], v[i * 8 + 5]);
+                            sq_acc2(qb[i], v[i * 8 + 6], v[i * 8 + 7]);
                         }
                         EPROF(asm volatile("" : "+l"(qa[0])); pr_sq += clock64() - p2;)
                     }
@@ -848,22 +703,10 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
             float2* exb = ex + (it & 1) * (NWG * 128);
             exb[wg * 128 + row] = make_float2(mx, sm);
             named_bar_sync(1, NWG * 128);
-            float M, own, S;
-            if constexpr (NWG == 2) {
-                const float2 o = exb[(wg ^ 1) * 128 + row];
-                M = fmaxf(mx, o.x);
-                own = ex2_approx(mx - M);
-                S = sm * own + o.y * ex2_approx(o.x - M);
-            } else {
-                float2 o[NWG];
-                M = mx;
-#pragma unroll
-                for (int w = 0; w < NWG; w++) { o[w] = exb[w * 128 + row]; M = fmaxf(M, o[w].x); }
-                own = ex2_approx(mx - M);
-                S = 0.f;
-#pragma unroll
-                for (int w = 0; w < NWG; w++) S += o[w].y * ex2_approx(o[w].x - M);
-            }
+            const float2 o = exb[(wg ^ 1) * 128 + row];
+            const float M = fmaxf(mx, o.x);
+            const float own = ex2_approx(mx - M);
+            const float S = sm * own + o.y * ex2_approx(o.x - M);
             const float denom = fmaf(M, kLn2, logf(S));              // :490-494, back in natural units
             const float scale = own / S;                             // exp(l - denom) = 2^(l2 - mx) * 2^(mx - M) / S
             EPROF(const long long p4 = clock64(); pr_lse += p4 - p3;)
@@ -901,8 +744,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
             ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 1);
             if (lane == 0) atomicAdd(ll_out, ll_acc);
         }
-          }
-}
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc<512>(tmem);
@@ -965,11 +807,12 @@ struct TcState {
     float* d_shift_f = nullptr;      // [32]
     float* d_inv_scale_f = nullptr;  // [32]
     double* d_scale = nullptr;       // [32] = 1 / inv_scale_f (double)
-    double* d_scratch = nullptr;
+    float* d_scratch = nullptr;      // [CTAs][MT][128][64] per-CTA partial sums, written once per launch
     size_t scratch_floats = 0;
-    size_t scratch_clean_bytes = 0;  // leading bytes of d_scratch known to be zero
-    size_t scratch_dirty_bytes = 0;  // bytes the last M-step launch wrote
     bool have_shift = false;
+    bool mstep_ready = false;        // the fixed-point quanta of the feature rows are set and inside the supported range
+    float zmax[GMM_MAX_DIMENSIONS] = {0};    // power-of-two bound of |z_d| over the whole data set
+    float magic[41 * 8] = {0};       // rounding constants of the feature rows (MMagic)
     // E-step
     CUtensorMap tm_x128{};
     bool emap_ok = false;
@@ -986,11 +829,8 @@ struct TcState {
     int e_ck_len = 0;                // Kmax rounded up to whole passes of 64
     int e_NG = 0;
     int host_threads = 8;
-    bool estep_alt = false;          // experimental alternating-warpgroup E-step epilogue (GMM_ESTEP_ALT=1)
-    bool estep_wg4 = false;          // experimental four-warpgroup E-step epilogue (GMM_ESTEP_WG4=1)
-    int gamma_split = 2;             // M-step: FP16 hi/lo pair for the responsibilities: 0 never, 1 always, 2 by cluster size
     // cudaFuncAttributeMaxDynamicSharedMemorySize is per device: the "already set" flags live with the (per-device) state
-    bool attr_estep = false, attr_estep4 = false, attr_mstep = false;
+    bool attr_estep = false, attr_mstep = false;
     double h_shift[GMM_MAX_DIMENSIONS] = {0}, h_scale[GMM_MAX_DIMENSIONS] = {0};
 };
 
@@ -1038,8 +878,6 @@ int tc_create(TcState** out, const float* d_x_aos, const float* d_x_soa, int n, 
               cudaStream_t stream) {
     (void)stream;
     TcState* t = new TcState();
-    if (const char* alt = getenv("GMM_ESTEP_ALT")) t->estep_alt = atoi(alt) != 0;
-    if (const char* wg4 = getenv("GMM_ESTEP_WG4")) t->estep_wg4 = atoi(wg4) != 0;
     t->d_x = d_x_aos; t->d_x_soa = d_x_soa; t->d_memb = d_memb; t->memb_pitch = memb_pitch; t->n = n; t->D = D; t->Kmax = Kmax; t->num_sms = num_sms;
     *out = t;
     if (n <= 0 || !tc_mstep_supported(D, Kmax)) return GMM_OK;
@@ -1071,12 +909,18 @@ int tc_create(TcState** out, const float* d_x_aos, const float* d_x_soa, int n, 
     const int mt = (num_features(D) + 127) / 128;
     const int ytiles = (Kmax + kNCL - 1) / kNCL;
     t->scratch_floats = (size_t)num_sms * ytiles * mt * 128 * kNCL;
-    TC_CUDA_TRY(cudaMalloc(&t->d_scratch, sizeof(double) * t->scratch_floats));
+    TC_CUDA_TRY(cudaMalloc(&t->d_scratch, sizeof(float) * t->scratch_floats));
     return GMM_OK;
 }
 
 void tc_set_host_threads(TcState* t, int n) { if (t) t->host_threads = n < 1 ? 1 : n; }
-void tc_set_gamma_split(TcState* t, int mode) { if (t) t->gamma_split = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
+bool tc_mstep_ready(const TcState* t) { return t && t->maps_ok && t->have_shift && t->mstep_ready; }
+bool tc_estep_range_ok(const TcState* t) {
+    if (!t || !t->have_shift) return false;
+    for (int d = 0; d < t->D; d++)
+        if (!(t->zmax[d] <= 16384.0f)) return false;
+    return true;
+}
 
 void tc_destroy(TcState* t) {
     if (!t) return;
@@ -1087,7 +931,7 @@ void tc_destroy(TcState* t) {
     delete t;
 }
 
-int tc_set_shift_scale(TcState* t, double* shift, const double* scale, cudaStream_t stream) {
+int tc_set_shift_scale(TcState* t, double* shift, const double* scale, const double* xmin, const double* xmax, cudaStream_t stream) {
     if (!t || !t->maps_ok) return GMM_OK;
     float sf[GMM_MAX_DIMENSIONS] = {0}, isf[GMM_MAX_DIMENSIONS] = {0};
     double sc[GMM_MAX_DIMENSIONS] = {0};
@@ -1099,6 +943,30 @@ int tc_set_shift_scale(TcState* t, double* shift, const double* scale, cudaStrea
         sc[d] = 1.0 / (double)isf[d];
         t->h_shift[d] = shift[d];
         t->h_scale[d] = sc[d];
+        // power-of-two bound of |z_d| = |(x - shift) * inv_scale| over the data (float arithmetic of the kernels + slack)
+        const double za = std::fmax(std::fabs(xmax[d] - (double)sf[d]), std::fabs(xmin[d] - (double)sf[d])) * (double)isf[d] * (1.0 + 1e-6);
+        int e2 = 0;
+        if (za > 0 && std::isfinite(za)) { e2 = std::ilogb(za) + 1; }      // za < 2^e2
+        t->zmax[d] = std::isfinite(za) ? (float)std::ldexp(1.0, e2) : INFINITY;
+    }
+    // Fixed-point quanta of the M-step feature rows: q = bound * 2^-9, magic = 1.5 * 2^23 * q.  Data with outliers
+    // beyond 64 standard deviations would leave too few bits below the quantum for the bulk of the events: such a data
+    // set is served by the FP64 SIMT M-step instead (tc_mstep_ready() false; GMM_PATH_TENSOR reports it).
+    t->mstep_ready = true;
+    {
+        const int D = t->D, F = num_features(D);
+        for (int f = 0; f < 41 * 8; f++) {
+            double bound = 1.0;
+            if (f >= 1 && f <= D) bound = t->zmax[f - 1];
+            else if (f > D && f < F) {
+                const int tt = f - 1 - D;
+                const int i = tri_row(tt), j = tt - i * (i + 1) / 2;
+                bound = (double)t->zmax[i] * (double)t->zmax[j];
+            }
+            t->magic[f] = (float)(1.5 * 8388608.0 * bound / (double)(1 << kPhiBits));
+        }
+        for (int d = 0; d < D; d++)
+            if (!(t->zmax[d] <= 64.0f)) t->mstep_ready = false;
     }
     TC_CUDA_TRY(cudaMemcpyAsync(t->d_shift_f, sf, sizeof(sf), cudaMemcpyHostToDevice, stream));
     TC_CUDA_TRY(cudaMemcpyAsync(t->d_inv_scale_f, isf, sizeof(isf), cudaMemcpyHostToDevice, stream));
@@ -1300,22 +1168,8 @@ static int launch_estep_d(TcState* t, int K, double* d_ll, cudaStream_t stream) 
     using C = ECfg<D>;
     static_assert(C::SMEM_BYTES <= 232448, "shared memory budget");
     if (!t->attr_estep) {
-        TC_CUDA_TRY(cudaFuncSetAttribute(estep_tc_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        TC_CUDA_TRY(cudaFuncSetAttribute(estep_tc_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        TC_CUDA_TRY(cudaFuncSetAttribute(estep_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         t->attr_estep = true;
-    }
-    auto kernel = t->estep_alt ? estep_tc_kernel<D, true> : estep_tc_kernel<D, false>;
-    int threads = kEThreads, smem_bytes = C::SMEM_BYTES;
-    if (t->estep_wg4) {
-        using C4 = ECfg<D, 4>;
-        static_assert(C4::SMEM_BYTES <= 232448, "shared memory budget");
-        if (!t->attr_estep4) {
-            TC_CUDA_TRY(cudaFuncSetAttribute(estep_tc_kernel<D, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, C4::SMEM_BYTES));
-            t->attr_estep4 = true;
-        }
-        kernel = estep_tc_kernel<D, false, 4>;
-        threads = C4::THREADS;
-        smem_bytes = C4::SMEM_BYTES;
     }
     const int ntiles = (t->n + 127) / 128;
     int grid = t->num_sms;
@@ -1325,7 +1179,7 @@ static int launch_estep_d(TcState* t, int K, double* d_ll, cudaStream_t stream) 
     if (NP > 1 && !t->d_den) return fail(GMM_ERR_STATE, "tensor E-step: context was created for at most 64 clusters");
     for (int p = 0; p < NP; p++) {
         const int Kp = K - 64 * p < 64 ? K - 64 * p : 64;
-        kernel<<<grid, threads, smem_bytes, stream>>>(
+        estep_tc_kernel<D><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(
             t->d_x, t->d_bimg + (size_t)p * C::MAXSG * C::B_SG, t->d_ck + 128 * p, t->d_shift_f, t->d_inv_scale_f,
             t->d_memb + (size_t)(64 * p) * t->memb_pitch, t->memb_pitch, t->n, Kp, (Kp + C::GB - 1) / C::GB, d_ll,
             NP > 1 ? t->d_den + (size_t)p * t->memb_pitch : nullptr);
@@ -1348,19 +1202,14 @@ int tc_launch_estep(TcState* t, int K, double* d_ll, cudaStream_t stream) {
     }
 }
 
-// Clusters of at least this many (soft) events take the single-FP16 responsibilities under mode 2: the rounding is an
-// unbiased relative perturbation <= 2^-12 per weight, so the statistics of a cluster move by ~1.4e-4 / sqrt(n_eff),
-// n_eff >= N_k: below 3.1e-6 from here on (30x under the parity bar, the size of the FP32 noise already there).
-constexpr float kGammaSplitMinN = 2048.0f;
-
 template <int D>
-static int launch_mstep_d(TcState* t, int K, double* d_stats, cudaStream_t stream, float min_nk, int* pair_out) {
+static int launch_mstep_d(TcState* t, int K, double* d_stats, cudaStream_t stream) {
     using C = MCfg<D>;
     static_assert(C::SMEM_BYTES <= 232448, "shared memory budget");
     static_assert(C::TMEM_COLS <= 512, "TMEM budget");
+    static_assert(sizeof(MMagic<D>) <= sizeof(TcState::magic), "magic table");
     if (!t->attr_mstep) {
-        TC_CUDA_TRY(cudaFuncSetAttribute(mstep_tc_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        TC_CUDA_TRY(cudaFuncSetAttribute(mstep_tc_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        TC_CUDA_TRY(cudaFuncSetAttribute(mstep_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         t->attr_mstep = true;
     }
     int gx = t->num_sms;
@@ -1370,43 +1219,27 @@ static int launch_mstep_d(TcState* t, int K, double* d_stats, cudaStream_t strea
     const int gy = (K + kNCL - 1) / kNCL;
     if ((size_t)gx * gy * C::MT * 128 * kNCL > t->scratch_floats) return fail(GMM_ERR_STATE, "tensor M-step scratch too small");
     dim3 grid(gx, gy);
-    // the flush warps add into zeroed per-CTA slots; tc_mstep_cleanup() zeroes the scratch after the statistics have
-    // left for the host (off the critical path), so only a launch that finds it dirty pays for a memset in front
-    const size_t scratch_bytes = sizeof(double) * (size_t)gx * gy * C::MT * 128 * kNCL;
-    if (t->scratch_clean_bytes < scratch_bytes) TC_CUDA_TRY(cudaMemsetAsync(t->d_scratch, 0, scratch_bytes, stream));
-    const bool split = t->gamma_split == 1 || (t->gamma_split == 2 && !(min_nk >= kGammaSplitMinN));
-    if (pair_out) *pair_out = split ? 1 : 0;
-    if (split)
-        mstep_tc_kernel<D, true><<<grid, kMThreads, C::SMEM_BYTES, stream>>>(t->tm_x, t->tm_g, t->n, t->d_scratch, per);
-    else
-        mstep_tc_kernel<D, false><<<grid, kMThreads, C::SMEM_BYTES, stream>>>(t->tm_x, t->tm_g, t->n, t->d_scratch, per);
+    MMagic<D> mg;
+    std::memcpy(mg.m, t->magic, sizeof(mg.m));
+    mstep_tc_kernel<D><<<grid, kMThreads, C::SMEM_BYTES, stream>>>(t->tm_x, t->tm_g, t->n, t->d_scratch, per, mg);
     TC_CUDA_TRY(cudaGetLastError());
     const int F = C::F;
     mstep_tc_finalize_kernel<<<F, 256, 0, stream>>>(t->d_scratch, gx, C::MT, K, D, F, t->d_scale, d_stats);
     TC_CUDA_TRY(cudaGetLastError());
-    t->scratch_dirty_bytes = scratch_bytes;
-    t->scratch_clean_bytes = 0;
     return GMM_OK;
 }
 
-int tc_mstep_cleanup(TcState* t, cudaStream_t stream) {
-    if (!t || !t->d_scratch || t->scratch_dirty_bytes == 0) return GMM_OK;
-    TC_CUDA_TRY(cudaMemsetAsync(t->d_scratch, 0, t->scratch_dirty_bytes, stream));
-    t->scratch_clean_bytes = t->scratch_dirty_bytes;
-    t->scratch_dirty_bytes = 0;
-    return GMM_OK;
-}
-
-int tc_launch_mstep(TcState* t, int K, double* d_stats, cudaStream_t stream, float min_nk, int* pair_out) {
+int tc_launch_mstep(TcState* t, int K, double* d_stats, cudaStream_t stream) {
     if (!t || !t->maps_ok) return fail(GMM_ERR_STATE, "tensor-core M-step not initialised for this shape");
     if (!t->have_shift) return fail(GMM_ERR_STATE, "tensor-core M-step needs gmm_seed (shift/scale) first");
+    if (!t->mstep_ready) return fail(GMM_ERR_STATE, "tensor-core M-step: the data range exceeds the fixed-point operand budget");
     switch (t->D) {
-        case 4: return launch_mstep_d<4>(t, K, d_stats, stream, min_nk, pair_out);
-        case 8: return launch_mstep_d<8>(t, K, d_stats, stream, min_nk, pair_out);
-        case 12: return launch_mstep_d<12>(t, K, d_stats, stream, min_nk, pair_out);
-        case 16: return launch_mstep_d<16>(t, K, d_stats, stream, min_nk, pair_out);
-        case 20: return launch_mstep_d<20>(t, K, d_stats, stream, min_nk, pair_out);
-        case 24: return launch_mstep_d<24>(t, K, d_stats, stream, min_nk, pair_out);
+        case 4: return launch_mstep_d<4>(t, K, d_stats, stream);
+        case 8: return launch_mstep_d<8>(t, K, d_stats, stream);
+        case 12: return launch_mstep_d<12>(t, K, d_stats, stream);
+        case 16: return launch_mstep_d<16>(t, K, d_stats, stream);
+        case 20: return launch_mstep_d<20>(t, K, d_stats, stream);
+        case 24: return launch_mstep_d<24>(t, K, d_stats, stream);
         default: return fail(GMM_ERR_ARG, "tensor-core M-step: unsupported D");
     }
 }

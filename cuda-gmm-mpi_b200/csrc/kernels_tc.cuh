@@ -17,12 +17,15 @@ int  tc_create(TcState** out, const float* d_x_aos, const float* d_x_soa, int n,
                int num_sms, cudaStream_t stream);
 void tc_destroy(TcState*);
 void tc_set_host_threads(TcState*, int n);
-// M-step responsibilities as an FP16 hi/lo pair (1), as one round-to-nearest FP16 value (0), or chosen per launch
-// from the smallest cluster size the caller passes to tc_launch_mstep (2, default: pair below 2048 events).
-void tc_set_gamma_split(TcState*, int mode);
 // Centre/scale used inside the tensor kernels: z = (x - shift) * inv_scale, both rounded to
-// float; `shift` is updated in place to the float-rounded values actually used.
-int  tc_set_shift_scale(TcState*, double* shift, const double* scale, cudaStream_t stream);
+// float; `shift` is updated in place to the float-rounded values actually used.  xmin / xmax: per-dimension extremes
+// of the WHOLE data set (all ranks): they fix the power-of-two quanta of the M-step's fixed-point operand parts.
+int  tc_set_shift_scale(TcState*, double* shift, const double* scale, const double* xmin, const double* xmax, cudaStream_t stream);
+// True once the quanta are set and the data range fits the fixed-point budget (|z| <= 64 global standard deviations);
+// otherwise the caller uses the FP64 SIMT M-step.
+bool tc_mstep_ready(const TcState*);
+// False when an event lies beyond 2^14 global standard deviations (its standardised coordinates would overflow FP16).
+bool tc_estep_range_ok(const TcState*);
 int  tc_upload_params(TcState*, const clusters_t* host, int K, cudaStream_t stream);
 // The same in three steps, so that the caller can fuse the per-cluster work with its own per-cluster
 // finalisation in ONE parallel loop: begin (serial), cluster k in [0, tc_params_padded) (independent, thread
@@ -33,11 +36,6 @@ int  tc_params_cluster(TcState*, const clusters_t* host, int k, int K);
 int  tc_params_commit(TcState*, int K, int bad, cudaStream_t stream);
 int  tc_launch_estep(TcState*, int K, double* d_ll, cudaStream_t stream);
 // Accumulates sum_n g[k][n] * phi_f(x_n - shift) into d_stats[k*F + f] (double, original units).
-// min_nk: smallest N_k of the current parameters (global, all ranks); only read under gamma-split mode 2.
-// *pair_out (optional): 1 when the FP16-pair kernel (three products) ran, 0 for the single-FP16 one (two products).
-int  tc_launch_mstep(TcState*, int K, double* d_stats, cudaStream_t stream, float min_nk, int* pair_out = nullptr);
-// Zeroes the per-CTA scratch of the last tc_launch_mstep for the next one; meant to be enqueued behind the D2H copy
-// of the statistics so that it runs while the host finalises.
-int  tc_mstep_cleanup(TcState*, cudaStream_t stream);
+int  tc_launch_mstep(TcState*, int K, double* d_stats, cudaStream_t stream);
 
 }  // namespace gmm

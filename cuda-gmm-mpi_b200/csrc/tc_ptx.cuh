@@ -23,6 +23,19 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrive whose issue DEPENDS on `dep`: the arrival count operand is selected by a comparison of dep's bit pattern with
+// one that no finite or infinite sum produces (a signalling NaN), so it is always 1 — but neither ptxas nor the hardware
+// can know that, and the arrive cannot issue before dep (and every load dep was computed from) is in its register.
+// Used to hand a shared-memory stage back to a producer only after this warp's loads from it have landed: a plain
+// mbarrier.arrive does not wait for the warp's outstanding LDS (measured in round 1).
+__device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, float dep) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 cnt;\n\t"
+        "setp.ne.b32 p, %1, 0xff800001;\n\t"
+        "selp.b32 cnt, 1, 2, p;\n\t"
+        "mbarrier.arrive.shared::cta.b64 _, [%0], cnt;\n\t}"
+        ::"r"(smem_u32(bar)), "r"(__float_as_uint(dep)) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }

@@ -265,8 +265,8 @@ class Engine:
     def profile(self, reset=False):
         out = (C.c_double * 8)()
         _check(self.lib.gmm_get_profile(self.h, out, int(reset)))
-        keys = ("estep_ms", "mstep_ms", "constants_host_ms", "allreduce_ms", "upload_ms", "mstep_pair_launches", "iterations",
-                "mstep_single_launches")
+        keys = ("estep_ms", "mstep_ms", "constants_host_ms", "allreduce_ms", "upload_ms", "mstep_tensor_launches", "iterations",
+                "mstep_simt_launches")
         return dict(zip(keys, list(out)[:8]))
 
     def fit_profile(self):

@@ -19,4 +19,8 @@ for lib in libs:
     env = dict(os.environ)
     if lib != "default": env["GMM_B200_LIB"] = os.path.abspath(lib)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
-    print(lib, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-500:])
+    lines = r.stdout.strip().splitlines()
+    for ln in lines[:-1]:
+        if "profile" in ln:
+            print("   ", ln)
+    print(lib, lines[-1] if lines else r.stderr[-500:])

@@ -28,9 +28,9 @@ def blobs(pkg, N, D, nb, sd):
 
 def pack(cl, prefix, out, memb=True):
     for f in FIELDS:
-        out[prefix + f] = getattr(cl, f)
+        out[prefix + f] = getattr(cl, f).copy()
     if memb and cl.memberships is not None:
-        out[prefix + "memb"] = cl.memberships
+        out[prefix + "memb"] = cl.memberships.copy()
 
 
 def unpack(pkg, z, prefix, K, D, N=0):
@@ -78,8 +78,8 @@ def run(tag, with_time):
         ev = blobs(pkg, N, D, nb, sd)
         ref = unpack(pkg, z, f"run_{name}_", K, D, N)
         for mix, (pe, pm) in mixes.items():
-            if name != "c1" and mix != "tt":
-                continue
+            if D < 8 and mix != "tt":
+                continue                                  # no tensor E-step below D = 8: the mixes coincide
             with pkg.Engine(ev, K) as eng:
                 eng.set_option("path", pkg.PATH_AUTO); eng.set_option("estep_path", pe); eng.set_option("mstep_path", pm)
                 eng.seed(K); eng.em(K, iters, iters)
@@ -89,23 +89,20 @@ def run(tag, with_time):
         ev = pkg.synth.make_blobs(N, D, min(K, 16), seed=300 + D)
         start = unpack(pkg, z, f"call_{name}_start_", K, D)
         ref = unpack(pkg, z, f"call_{name}_", K, D)
-        for gs in (1, 0):
-            with pkg.Engine(ev, K) as eng:
-                eng.set_option("path", pkg.PATH_TENSOR); eng.set_option("estep_path", pkg.PATH_SIMT); eng.set_option("mstep_gamma_split", gs)
-                eng.seed(K); eng.set_clusters(K, start); eng.estep(K); eng.mstep(K); eng.constants(K)
-                got = eng.get_clusters(K)
-            out[f"call_{name}_gs{gs}"] = dev(got, ref, K)
+        with pkg.Engine(ev, K) as eng:
+            eng.set_option("path", pkg.PATH_TENSOR); eng.set_option("estep_path", pkg.PATH_SIMT)
+            eng.seed(K); eng.set_clusters(K, start); eng.estep(K); eng.mstep(K); eng.constants(K)
+            got = eng.get_clusters(K)
+        out[f"call_{name}"] = dev(got, ref, K)
     if with_time:
         N, D, K = 4_000_000, 24, 64
         ev = pkg.synth.make_blobs(N, D, K)
         with pkg.Engine(ev, K) as eng:
             eng.seed(K); eng.estep(K)
-            for gs in (1, 0):
-                eng.set_option("mstep_gamma_split", gs)
-                eng.em_iterations(K, 3); eng.profile(reset=True)
-                eng.em_iterations(K, 10)
-                p = eng.profile(reset=True)
-                out[f"time_4M_gs{gs}"] = {k: round(float(v) / 10, 4) for k, v in p.items() if k in ("estep_ms", "mstep_ms")}
+            eng.em_iterations(K, 3); eng.profile(reset=True)
+            eng.em_iterations(K, 10)
+            p = eng.profile(reset=True)
+            out["time_4M"] = {k: round(float(v) / 10, 4) for k, v in p.items() if k in ("estep_ms", "mstep_ms")}
     print(json.dumps(out))
 
 

@@ -183,29 +183,61 @@ def test_mstep_tensor_path_large(loaded, oracle64, N, D, K):
     assert_params_close(got, ref, K)
 
 
-@pytest.mark.parametrize("mode", [2, 0, 1])
-def test_mstep_tensor_gamma_modes_large_clusters(loaded, oracle64, mode):
-    """Tensor M-step with clusters of 50k-180k events: mode 2 (default) picks the single-FP16 responsibilities here
-    (every N_k >= 2048), mode 0 forces them, mode 1 forces the hi/lo pair — all inside the per-call 1e-4 bar."""
+def test_mstep_tensor_large_clusters_and_outliers(loaded, oracle64):
+    """Tensor M-step with clusters of 50k-180k events (long exact accumulation chains: every 128-event chain of a big
+    cluster is close to the 2^24-quanta budget) and with a few far outliers in the data (they widen the fixed-point
+    quanta of the feature rows: the statistics stay unbiased, inside the per-call 1e-4 bar)."""
     pkg = loaded
     N, D, K = 400_000, 24, 3
     ev = pkg.synth.make_blobs(N, D, K, seed=808)
+    for variant in ("plain", "outliers"):
+        if variant == "outliers":
+            ev = ev.copy()
+            ev[1000] += 150.0                  # ~25 global standard deviations away
+            ev[250_000, 3] -= 200.0
+        ref = fitted_params(pkg, oracle64, ev, K, iters=2)
+        soa = oracle64.transpose(ev)
+        with pkg.Engine(ev, K) as eng:
+            eng.set_option("path", pkg.PATH_TENSOR)
+            eng.seed(K)
+            eng.set_clusters(K, ref)
+            eng.estep(K)
+            eng.mstep(K)
+            eng.constants(K)
+            got = eng.get_clusters(K)
+            assert eng.profile()["mstep_tensor_launches"] == 1
+        oracle64.estep(soa, ref, K)
+        oracle64.mstep(soa, ref, K)
+        oracle64.constants(ref, K)
+        assert_params_close(got, ref, K)
+
+
+def test_mstep_extreme_outlier_uses_fp64_kernel(loaded, oracle64):
+    """An outlier beyond 64 global standard deviations leaves the tensor M-step's fixed-point budget: GMM_PATH_AUTO runs
+    the FP64 SIMT M-step for that data set (per-call parity unchanged), GMM_PATH_TENSOR reports the condition."""
+    pkg = loaded
+    N, D, K = 50_000, 8, 4
+    ev = pkg.synth.make_blobs(N, D, K, seed=99).copy()
+    ev[77, 2] += 1.0e5
     ref = fitted_params(pkg, oracle64, ev, K, iters=2)
-    assert ref.N.min() >= 2048
     soa = oracle64.transpose(ev)
     with pkg.Engine(ev, K) as eng:
-        eng.set_option("path", pkg.PATH_TENSOR)
-        eng.set_option("mstep_gamma_split", mode)
         eng.seed(K)
         eng.set_clusters(K, ref)
         eng.estep(K)
         eng.mstep(K)
         eng.constants(K)
         got = eng.get_clusters(K)
+        p = eng.profile()
+        assert p["mstep_tensor_launches"] == 0 and p["mstep_simt_launches"] == 1
     oracle64.estep(soa, ref, K)
     oracle64.mstep(soa, ref, K)
     oracle64.constants(ref, K)
     assert_params_close(got, ref, K)
+    with pkg.Engine(ev, K) as eng:
+        eng.set_option("path", pkg.PATH_TENSOR)
+        with pytest.raises(pkg.GmmError):
+            eng.seed(K)
 
 
 @pytest.mark.parametrize("path", PATHS)
