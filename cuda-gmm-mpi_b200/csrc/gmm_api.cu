@@ -8,8 +8,11 @@
 // CUDA device of compute capability 10.x.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -445,7 +448,7 @@ int gmm_create(gmm_ctx** out, int device, int n_local, int D, int Kmax, const fl
     *out = nullptr;
     if (D < 1 || D > GMM_MAX_DIMENSIONS) return fail(GMM_ERR_ARG, "gmm_create: D must be in [1,32] (gaussian.h:16)");
     if (Kmax < 1 || Kmax > GMM_MAX_CLUSTERS) return fail(GMM_ERR_ARG, "gmm_create: Kmax must be in [1,512] (gaussian.h:10)");
-    if (n_local < 0 || (n_local > 0 && !events_aos)) return fail(GMM_ERR_ARG, "gmm_create: bad events");
+    if (n_local < 0) return fail(GMM_ERR_ARG, "gmm_create: bad events");   // events_aos == NULL: supplied later (gmm_upload_events*)
     if (n_global <= 0) n_global = n_local;
     if (n_global < 1) return fail(GMM_ERR_ARG, "gmm_create: no events");
     int ndev = 0;
@@ -492,7 +495,7 @@ int gmm_create(gmm_ctx** out, int device, int n_local, int D, int Kmax, const fl
     CREATE_TRY(cudaMallocHost(&c->h_stats, sizeof(double) * ((size_t)Kmax * c->F + 1)));
     CREATE_TRY(cudaMalloc(&c->d_shift, sizeof(double) * GMM_MAX_DIMENSIONS));
     CREATE_TRY(cudaMemsetAsync(c->d_shift, 0, sizeof(double) * GMM_MAX_DIMENSIONS, c->stream));
-    if (n_local > 0) {
+    if (n_local > 0 && events_aos) {
         CREATE_TRY(cudaMemcpyAsync(c->d_x_aos, events_aos, sizeof(float) * (size_t)n_local * D, cudaMemcpyHostToDevice, c->stream));
         dim3 blk(32, 8);
         transpose_aos_to_soa_kernel<<<(n_local + 31) / 32, blk, 0, c->stream>>>(c->d_x_aos, c->d_x_soa, c->memb_pitch, n_local, D);
@@ -528,6 +531,63 @@ int gmm_upload_events(gmm_ctx* c, const float* events_aos) {
     c->estep_tensor_ready = false;
     c->cur_K = 0;
     return GMM_OK;
+}
+
+// The shard's rows of a "*.bin" file (readData.cpp:35-47 format) straight to the device: pread into two pinned
+// staging buffers, each chunk's H2D copy overlapping the read of the next (replaces whole-file malloc + fread on the
+// host, gaussian.cu:188-218, followed by a pageable copy per GPU, :360-377).
+int gmm_upload_events_file(gmm_ctx* c, const char* path) {
+    if (!c || !path) return fail(GMM_ERR_ARG, "gmm_upload_events_file: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(GMM_ERR_IO, std::string("cannot open ") + path);
+    int32_t hdr[2] = {0, 0};
+    if (pread(fd, hdr, sizeof(hdr), 0) != (ssize_t)sizeof(hdr) || hdr[0] <= 0 || hdr[1] != c->D || (long long)hdr[0] != c->n_global) {
+        close(fd);
+        return fail(GMM_ERR_IO, "gmm_upload_events_file: header does not match the context (events / dimensions)");
+    }
+    const size_t row = sizeof(float) * (size_t)c->D;
+    const size_t total = row * (size_t)c->n;
+    const size_t chunk = std::max<size_t>(row, ((size_t)32 << 20) / row * row);
+    char* stage[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    int rc = GMM_OK;
+    for (int b = 0; b < 2 && rc == GMM_OK; b++) {
+        if (cudaMallocHost(&stage[b], chunk) != cudaSuccess || cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming) != cudaSuccess)
+            rc = fail(GMM_ERR_CUDA, "gmm_upload_events_file: pinned staging allocation failed");
+    }
+    size_t off = 0;
+    for (int i = 0; rc == GMM_OK && off < total; i++) {
+        const int b = i & 1;
+        const size_t len = std::min(chunk, total - off);
+        if (i >= 2 && cudaEventSynchronize(done[b]) != cudaSuccess) { rc = fail(GMM_ERR_CUDA, "gmm_upload_events_file: copy failed"); break; }
+        size_t got = 0;
+        while (got < len) {
+            const ssize_t r = pread(fd, stage[b] + got, len - got, (off_t)(sizeof(hdr) + row * (size_t)c->offset + off + got));
+            if (r <= 0) { rc = fail(GMM_ERR_IO, "truncated .bin file"); break; }
+            got += (size_t)r;
+        }
+        if (rc != GMM_OK) break;
+        if (cudaMemcpyAsync(reinterpret_cast<char*>(c->d_x_aos) + off, stage[b], len, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+            cudaEventRecord(done[b], c->stream) != cudaSuccess) { rc = fail(GMM_ERR_CUDA, "gmm_upload_events_file: copy failed"); break; }
+        off += len;
+    }
+    close(fd);
+    if (rc == GMM_OK && c->n > 0) {
+        dim3 blk(32, 8);
+        transpose_aos_to_soa_kernel<<<(c->n + 31) / 32, blk, 0, c->stream>>>(c->d_x_aos, c->d_x_soa, c->memb_pitch, c->n, c->D);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(GMM_ERR_CUDA, "transpose launch failed");
+    }
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && rc == GMM_OK) rc = fail(GMM_ERR_CUDA, "gmm_upload_events_file: copy failed");
+    for (int b = 0; b < 2; b++) {
+        if (stage[b]) cudaFreeHost(stage[b]);
+        if (done[b]) cudaEventDestroy(done[b]);
+    }
+    c->have_shift = false;
+    c->memb_valid = false;
+    c->estep_tensor_ready = false;
+    c->cur_K = 0;
+    return rc;
 }
 
 void gmm_destroy(gmm_ctx* c) {

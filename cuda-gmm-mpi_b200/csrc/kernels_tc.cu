@@ -12,19 +12,22 @@
 // Operand arithmetic (round 2).  The FP32 accumulation in TMEM truncates toward zero (tc_probe T2/T7) — but it
 // is EXACT as long as every partial sum is a multiple of one quantum and fits 24 bits (tc_probe T8).  The
 // operands are therefore split into a FIXED-POINT leading part and a small remainder:
-//     phi_f = ph + pl,   ph = q_f * round(phi_f / q_f),   |ph| <= 2^9 q_f      (q_f: power of two per feature row,
+//     phi_f = ph + pl,   ph = q_f * round(phi_f / q_f),   |ph| <= 2^11 q_f     (q_f: power of two per feature row,
 //                                                                              from the data's largest |z_d|)
-//     g     = gh + gl,   gh = 2^-8 * round(2^8 g)   (0 .. 256 quanta)
+//     g     = gh + gl,   gh = 2^-6 * round(2^6 g)   (0 .. 64 quanta)
 // (both by a magic-number add: no conversion round trip), and the products go to two accumulators per
 // 128-row feature tile:
-//     columns [0, 64):    sum ph * gh                 — every product a multiple of q_f 2^-8, at most 2^17 quanta;
+//     columns [0, 64):    sum ph * gh                 — every product a multiple of q_f 2^-6, at most 2^17 quanta;
 //                                                       128 events per chain: <= 2^24 quanta: NO rounding at all
-//     columns [64, 128):  sum ph * gl + pl * gh       — 2^-8 of the magnitude; its truncation bias (~1e-6 relative
-//                                                       to itself) is 1e-8 .. 1e-9 of the statistic
+//     columns [64, 128):  sum ph * gl + pl * gs       — gs = g rounded once to FP16 (11 bits RELATIVE): with gh alone
+//                                                       the dropped pl * gl would be O(pl / phi) of every event whose
+//                                                       g is below the quantum (measured: 1.6e-4 on covariances);
+//                                                       ~1 % of the magnitude, its truncation bias (~1e-6 relative to
+//                                                       itself) is 1e-8 of the statistic
 // The raw-moment cancellation |mu - shift|^2 / sigma^2 ~ 100 that amplified the old split's systematic error
 // (1.5e-3 on responsibilities after 100 EM iterations) now multiplies unbiased rounding noise only.
 // With B = [gh ; gl] stacked as ONE N = 128 operand, ph x [gh ; gl] is a single MMA at the tensor pipe's math
-// rate (64 cycles; N = 64 runs at 49.8, operand-fetch bound) that fills both column groups; pl x gh (N = 64)
+// rate (64 cycles; N = 64 runs at 49.8, operand-fetch bound) that fills both column groups; pl x gs (N = 64)
 // adds into the second group: 114 instead of 149 cycles per (tile, k-step) and 14 instead of 18 KB of operand
 // fetch.
 //
@@ -79,11 +82,15 @@ constexpr int kTE = 32;          // events per sub-tile (MMA K extent per operan
 constexpr int kNCL = 64;         // clusters per CTA pass
 constexpr int kNST = 3;          // operand stages
 constexpr int kNRAW = 4;         // raw (TMA) stages
-constexpr int kChunkSub = 4;     // sub-tiles per accumulation chain: 128 events (the exactness budget above)
+constexpr int kChunkSub = 4;     // sub-tiles per chain of the exact column group: 128 events (the bit budget below)
+constexpr int kChunkSub2 = 16;   // sub-tiles per chain of the remainder column group (no exactness to protect: drained 4x less often)
 constexpr int kMThreads = 512;
-constexpr int kPhiBits = 9;      // |ph| <= 2^9 quanta
+// Bit budget of the exact accumulator: 11 (ph, every integer up to 2048 is an FP16 value) + 6 (gh) + 7 (128 events) = 24.
+// The split favours phi: the remainder pl is rounded to FP16 RELATIVE to itself, so its (unbiased) rounding noise scales
+// with the quantum of ph — on covariance entries 6e-6 per call with 9 + 8 bits, 1.2e-6 with 11 + 6 (scripts/emu_mstep.py).
+constexpr int kPhiBits = 11;     // |ph| <= 2^11 quanta
 constexpr float kGammaScale = 1024.0f;               // responsibilities are scaled by 2^10 in the operand
-constexpr float kGammaMagic = 1.5f * 33554432.0f;    // 1.5 * 2^25: ulp = 4 = 2^-8 in the scaled units
+constexpr float kGammaMagic = 1.5f * 134217728.0f;   // 1.5 * 2^27: ulp = 16 = 2^-6 in the scaled units
 
 template <int D> struct MCfg {
     static constexpr int F = 1 + D + D * (D + 1) / 2;
@@ -92,7 +99,7 @@ template <int D> struct MCfg {
     static constexpr int PHI_PART = MT * 128 * kTE * 2;   // bytes of one part (leading or remainder)
     static constexpr int PHI_STAGE = 2 * PHI_PART;
     static constexpr int G_PART = kNCL * kTE * 2;
-    static constexpr int G_STAGE = 2 * G_PART;            // [gh (64 rows) ; gl (64 rows)] = ONE K-major N = 128 image
+    static constexpr int G_STAGE = 3 * G_PART;            // [gh (64 rows) ; gl (64 rows)] = ONE K-major N = 128 image, then gs
     static constexpr int RAWX = D * kTE * 4;              // [D][32 events] from the SoA copy
     static constexpr int RAWG = kNCL * kTE * 4;
     static constexpr int OFF_PHI = 0;
@@ -154,7 +161,7 @@ __device__ __forceinline__ void build_phi_chunks(const float (&z)[D], const MMag
 #pragma unroll
         for (int u = 0; u < 8; u++) feature_split<D>(z, c * 8 + u, mg.m[c * 8 + u], hi[u], lo[u]);
         uint4 h, l;
-        h.x = pack_half2(hi[0], hi[1]); h.y = pack_half2(hi[2], hi[3]); h.z = pack_half2(hi[4], hi[5]); h.w = pack_half2(hi[6], hi[7]);   // exact: <= 10 bits
+        h.x = pack_half2(hi[0], hi[1]); h.y = pack_half2(hi[2], hi[3]); h.z = pack_half2(hi[4], hi[5]); h.w = pack_half2(hi[6], hi[7]);   // exact: <= 2048 quanta
         l.x = pack_half2(lo[0], lo[1]); l.y = pack_half2(lo[2], lo[3]); l.z = pack_half2(lo[4], lo[5]); l.w = pack_half2(lo[6], lo[7]);
         *reinterpret_cast<uint4*>(hi_base + c * 512 + eoff) = h;
         *reinterpret_cast<uint4*>(lo_base + c * 512 + eoff) = l;
@@ -163,8 +170,11 @@ __device__ __forceinline__ void build_phi_chunks(const float (&z)[D], const MMag
 
 // Feature tile `mt` is drained after sub-tile i when its 128-event chain ends there: the chains of the tiles are
 // staggered by one sub-tile each, so that only one tile is being drained at a time (single-buffered accumulators).
+// The remainder column group rides along and is drained (and restarted) only at every fourth of those points.
 __device__ __forceinline__ bool chain_ends(int i, int mt, int nsub) { return ((i + mt) % kChunkSub) == kChunkSub - 1 || i == nsub - 1; }
 __device__ __forceinline__ bool chain_starts(int i, int mt) { return i == 0 || ((i + mt) % kChunkSub) == 0; }
+__device__ __forceinline__ bool chain2_ends(int i, int mt, int nsub) { return ((i + mt) % kChunkSub2) == kChunkSub2 - 1 || i == nsub - 1; }
+__device__ __forceinline__ bool chain2_starts(int i, int mt) { return i == 0 || ((i + mt) % kChunkSub2) == 0; }
 
 template <int D>
 __global__ void __launch_bounds__(kMThreads, 1)
@@ -233,7 +243,7 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 const uint32_t gam = smem_u32(smem + C::OFF_G + os * C::G_STAGE);
 #pragma unroll
                 for (int mt = 0; mt < C::MT; mt++) {
-                    const bool first = chain_starts(i, mt);
+                    const bool first = chain_starts(i, mt), first2 = chain2_starts(i, mt);
                     if (first && ((used >> mt) & 1u)) {        // the previous chain of this tile must have been drained
                         mbar_wait_parked(&acc_empty[mt], (drained >> mt) & 1u, 100);
                         drained ^= 1u << mt;
@@ -243,10 +253,17 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 #pragma unroll
                     for (int ks = 0; ks < kTE / 16; ks++) {
                         const uint64_t bdesc = make_smem_desc(gam + ks * 256, /*LBO*/ 128, /*SBO*/ 512);     // rows 0-63 gh, 64-127 gl
+                        const uint64_t sdesc = make_smem_desc(gam + 2 * C::G_PART + ks * 256, 128, 512);     // gs
                         const uint64_t ah = make_smem_desc(phi + mt * 8192 + ks * 256, /*LBO*/ 128, /*SBO*/ 512);
                         const uint64_t al = make_smem_desc(phi + C::PHI_PART + mt * 8192 + ks * 256, 128, 512);
-                        mma_f16_ss(dcol, ah, bdesc, idesc128, !(first && ks == 0));     // [ph gh | ph gl]
-                        mma_f16_ss(dcol + kNCL, al, bdesc, idesc64, true);             //          += pl gh
+                        if (first && !first2 && ks == 0) {     // restart the exact group only: the two halves as separate N = 64 steps
+                            const uint64_t ldesc = make_smem_desc(gam + C::G_PART + ks * 256, 128, 512);
+                            mma_f16_ss(dcol, ah, bdesc, idesc64, false);                //  ph gh
+                            mma_f16_ss(dcol + kNCL, ah, ldesc, idesc64, true);          //          += ph gl
+                        } else {
+                            mma_f16_ss(dcol, ah, bdesc, idesc128, !(first && ks == 0)); // [ph gh | ph gl]
+                        }
+                        mma_f16_ss(dcol + kNCL, al, sdesc, idesc64, true);             //          += pl gs
                     }
                     if (chain_ends(i, mt, nsub)) { mma_commit(&acc_full[mt]); used |= 1u << mt; }
                 }
@@ -278,7 +295,7 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             // c ^ (r & 7)), so 8 lanes reading the same chunk of 8 consecutive rows hit 8 different
             // bank groups; the operand image puts the 4 K-chunks of an 8-row group next to each other
             // (LBO = 128, SBO = 512), so a warp stores 512 contiguous bytes: no bank conflicts either way.
-            uint4 gh[2], gl[2];
+            uint4 gh[2], gl[2], gs[2];
             float gdep = 0.0f;
 #pragma unroll
             for (int it2 = 0; it2 < 2; it2++) {
@@ -292,12 +309,14 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 gdep += a.x + b.x;
                 float hi[8], lo[8];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {                  // gh = 4 * round(256 g) (0 .. 1024), gl = 1024 g - gh, both from the exact product
+                for (int u = 0; u < 8; u++) {                  // gh = 16 * round(64 g) (0 .. 1024), gl = 1024 g - gh, both from the exact product
                     hi[u] = __fsub_rn(__fmaf_rn(g[u], kGammaScale, kGammaMagic), kGammaMagic);
                     lo[u] = __fmaf_rn(g[u], kGammaScale, -hi[u]);
                 }
                 gh[it2] = make_uint4(pack_half2(hi[0], hi[1]), pack_half2(hi[2], hi[3]), pack_half2(hi[4], hi[5]), pack_half2(hi[6], hi[7]));
                 gl[it2] = make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]), pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7]));
+                gs[it2] = make_uint4(pack_half2(g[0] * kGammaScale, g[1] * kGammaScale), pack_half2(g[2] * kGammaScale, g[3] * kGammaScale),
+                                     pack_half2(g[4] * kGammaScale, g[5] * kGammaScale), pack_half2(g[6] * kGammaScale, g[7] * kGammaScale));
             }
             // The raw tiles must BE in registers before the stage goes back to the TMA producer: an mbarrier arrive does
             // not wait for the warp's outstanding LDS (measured in round 1: with nothing consuming the z loads before the
@@ -329,6 +348,7 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     const int kg = item >> 5, l = item & 31;
                     *reinterpret_cast<uint4*>(g_hi + kg * 512 + l * 16) = gh[it2];
                     *reinterpret_cast<uint4*>(g_hi + C::G_PART + kg * 512 + l * 16) = gl[it2];
+                    *reinterpret_cast<uint4*>(g_hi + 2 * C::G_PART + kg * 512 + l * 16) = gs[it2];
                 }
             }
             fence_proxy_async_smem();
@@ -352,14 +372,22 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 tc_fence_after();
                 const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + mt * 128;
 #pragma unroll
-                for (int b = 0; b < kNCL / 16; b++) {
-                    uint32_t a1[16], a2[16];
-                    tmem_ld_32x16(tbase + b * 16, a1);                 // exact leading products
-                    tmem_ld_32x16(tbase + kNCL + b * 16, a2);          // remainder products
+                for (int b = 0; b < kNCL / 32; b++) {              // exact leading products
+                    uint32_t a[32];
+                    tmem_ld_32x32(tbase + b * 32, a);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; j++)
-                        racc[mt * kNCL + b * 16 + j] += __uint_as_float(a1[j]) + __uint_as_float(a2[j]);
+                    for (int j = 0; j < 32; j++) racc[mt * kNCL + b * 32 + j] += __uint_as_float(a[j]);
+                }
+                if (chain2_ends(i, mt, nsub)) {
+#pragma unroll
+                    for (int b = 0; b < kNCL / 32; b++) {          // remainder products
+                        uint32_t a[32];
+                        tmem_ld_32x32(tbase + kNCL + b * 32, a);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; j++) racc[mt * kNCL + b * 32 + j] += __uint_as_float(a[j]);
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -949,7 +977,7 @@ int tc_set_shift_scale(TcState* t, double* shift, const double* scale, const dou
         if (za > 0 && std::isfinite(za)) { e2 = std::ilogb(za) + 1; }      // za < 2^e2
         t->zmax[d] = std::isfinite(za) ? (float)std::ldexp(1.0, e2) : INFINITY;
     }
-    // Fixed-point quanta of the M-step feature rows: q = bound * 2^-9, magic = 1.5 * 2^23 * q.  Data with outliers
+    // Fixed-point quanta of the M-step feature rows: q = bound * 2^-11, magic = 1.5 * 2^23 * q.  Data with outliers
     // beyond 64 standard deviations would leave too few bits below the quantum for the bulk of the events: such a data
     // set is served by the FP64 SIMT M-step instead (tc_mstep_ready() false; GMM_PATH_TENSOR reports it).
     t->mstep_ready = true;

@@ -57,6 +57,8 @@ def load_library():
     L.gmm_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                              C.c_longlong, C.c_longlong]
     L.gmm_upload_events.argtypes = [C.c_void_p, C.c_void_p]
+    L.gmm_upload_events_file.argtypes = [C.c_void_p, C.c_char_p]
+    L.gmm_read_bin_header.argtypes = [C.c_char_p, _IP, _IP]
     L.gmm_destroy.argtypes = [C.c_void_p]
     L.gmm_destroy.restype = None
     L.gmm_shard_range.argtypes = [C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
@@ -215,6 +217,9 @@ class Engine:
             assert events.shape == (self.n, self.D)
             events_ptr = events.ctypes.data
         _check(self.lib.gmm_upload_events(self.h, events_ptr))
+
+    def upload_events_file(self, path):
+        _check(self.lib.gmm_upload_events_file(self.h, os.fsencode(path)))
 
     def new_clusters(self, with_memberships=False):
         return Clusters(self.Kmax, self.D, self.n if with_memberships else 0)

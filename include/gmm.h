@@ -83,6 +83,15 @@ void gmm_destroy(gmm_ctx*);
  * of gaussian.cu:370 without re-creating buffers or the communicator.                        */
 int  gmm_upload_events(gmm_ctx*, const float* events_aos);
 
+/* The same from a "*.bin" file (readData.cpp:35-47: int32 N, int32 D, float32[N][D]): the rows
+ * [offset, offset + n_local) of the file go to the device through two pinned staging buffers,
+ * reads and H2D copies overlapped; the host never holds the data set (replaces readData +
+ * the host transpose + the per-GPU pageable copy, gaussian.cu:188-218, 360-377).  The header must
+ * match the context (N == n_global, D).  A context may be created with events_aos == NULL and
+ * filled this way.                                                                             */
+int  gmm_upload_events_file(gmm_ctx*, const char* path);
+int  gmm_read_bin_header(const char* path, int* ndims, int* nevents);
+
 /* Contiguous event range of shard `rank` of `nranks` (gaussian.cu:348-352,
  * with quirk Q6 fixed: the remainder goes to the LAST shard).              */
 void gmm_shard_range(long long n_global, int nranks, int rank,

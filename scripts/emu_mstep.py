@@ -58,3 +58,46 @@ def run(N, D, K, iters, seed=None):
 
 run(10000, 4, 8, 20)
 run(100000, 16, 32, 5)
+
+
+PHI_BITS, G_BITS = 11, 6
+
+
+def run_fixed(N, D, K, iters):
+    """The round-2 operand scheme: fixed-point leading parts (exact accumulation) + FP16 remainders."""
+    ev = pkg.synth.make_blobs(N, D, K)
+    ref = pkg.Clusters(K, D, N); o64.seed(ev, K, ref); o64.em(o64.transpose(ev), ref, K, iters, iters)
+    g = ref.memberships.astype(np.float32)
+    x = ev.astype(np.float64)
+    sf = x.mean(0).astype(np.float32); isf = (1.0 / x.std(0)).astype(np.float32)
+    z32 = ((ev - sf) * isf).astype(np.float32)
+    zz = z32.astype(np.float64); gd = g.astype(np.float64)
+    S0 = gd.sum(1); S1 = gd @ zz; S2 = np.einsum('kn,ni,nj->kij', gd, zz, zz)
+    cov_ref, m_ref = cov_from_stats(S0, S1, S2)
+    zmax = 2.0 ** (np.floor(np.log2(np.abs(zz).max(0) * (1 + 1e-6))) + 1)
+    f16 = lambda a: a.astype(np.float32).astype(np.float16).astype(np.float64)
+    def fsplit(v, bound):
+        q = bound / float(1 << PHI_BITS)
+        h = np.round(v / q) * q
+        return h, f16(v - h)
+    gh = np.round(gd * float(1 << G_BITS)) / float(1 << G_BITS)
+    gl = f16((gd - gh) * 1024.0) / 1024.0
+    gs = f16(gd * 1024.0) / 1024.0
+    zh, zl = fsplit(zz, zmax[None, :])
+    prod = zz[:, :, None] * zz[:, None, :]
+    ph, pl = fsplit(prod.reshape(N, D * D), (zmax[:, None] * zmax[None, :]).reshape(1, D * D))
+    one = np.ones((N, 1))
+    for name, rem in (("pl*gh (call B build)", gh), ("pl*gs", gs)):
+        def contract(fh, fl):
+            return gh @ fh + gl @ fh + rem @ fl
+        s0 = contract(one, 0 * one)[:, 0]
+        s1 = contract(zh, zl)
+        s2 = contract(ph, pl).reshape(K, D, D)
+        cov, m = cov_from_stats(s0, s1, s2)
+        dR = max(np.abs(cov[k] - cov_ref[k]).max() / np.abs(cov_ref[k]).max() for k in range(K))
+        print(f"  fixed-point, remainder product {name}: max rel cov err {dR:.2e}  dN {np.abs(s0 / S0 - 1).max():.2e}  dmean {np.abs(m - m_ref).max():.2e}")
+
+
+print("fixed-point scheme (exact accumulation emulated)")
+run_fixed(10000, 4, 8, 20)
+run_fixed(100000, 16, 32, 5)

@@ -225,3 +225,27 @@ def test_host_finalize_is_shift_invariant(pkg):
         np.testing.assert_allclose(o.means, outs[0].means, rtol=1e-6, atol=1e-5)
         np.testing.assert_allclose(o.R, outs[0].R, rtol=2e-4, atol=2e-4)      # shift 0 cancels |mu|^2 ~ 900 against sigma^2 ~ 1
         np.testing.assert_allclose(o.constant, outs[0].constant, rtol=1e-4)
+
+
+def test_results_writer_matches_printf(pkg, tmp_path):
+    """gmm_write_results formats with its own "%f" routine (parallel, buffered): digit for digit what printf gives,
+    ties, carries, signed zeros, huge values, inf / nan included (gaussian.cu:1044-1058 uses fprintf "%f")."""
+    rng = np.random.default_rng(1)
+    N, D, K = 5000, 5, 7
+    ev = (rng.standard_normal((N, D)) * 10.0 ** rng.integers(-8, 9, (N, 1))).astype(np.float32)
+    ev[0] = [0.0, -0.0, 1e-7, -1e-7, 0.9999995]
+    ev[1] = [2.5e-7, 3.5e-7, 0.0000005, 1.0000005, 123456789.0]
+    ev[2] = [1e14, -1e14, 3e15, 1e20, float("inf")]
+    ev[3] = [0.5e-6, 1.5e-6, 2.5e-6, -0.5e-6, -2.5e-6]
+    ev[4] = [3.4e38, -3.4e38, float("nan"), 1e-45, 16777216.0]
+    ev[5:105] = rng.integers(-3, 3, (100, D)) + 0.5
+    ev[105:205] = rng.integers(0, 1000, (100, D)) / 64.0
+    cl = pkg.Clusters(K, D, N)
+    cl.memberships[...] = rng.random((K, N)).astype(np.float32)
+    path = str(tmp_path / "t.results")
+    pkg.write_results(path, ev, cl, K)
+    lines = open(path).read().splitlines()
+    assert len(lines) == N
+    for i in range(N):
+        exp = ",".join("%f" % float(v) for v in ev[i]) + "\t" + ",".join("%f" % float(v) for v in cl.memberships[:, i])
+        assert lines[i] == exp, i
