@@ -430,7 +430,7 @@ def main():
                           peak_source=peaks["source"] + " dense bf16/fp16 sustained (the kernel issues kind::f16 MMAs)",
                           ms_per_launch=mstep_ms, algorithmic_flops_per_launch=m_flops,
                           executed_mma_flops_per_launch=exec_flops, executed_tflops=exec_flops / (mstep_ms * 1e-3) / 1e12 if mstep_ms > 0 else 0.0,
-                          kernel=dict(mstep_tc_kernel_launches=n_tensor, mstep_simt_kernel_launches=n_simt,
+                          kernels=dict(mstep_tc_kernel_launches=n_tensor, mstep_simt_kernel_launches=n_simt,
                                       note="launch counts in the timed region; mstep_tc_kernel = fixed-point leading parts (exact TMEM "
                                            "accumulation) + FP16 remainders, three products per element"))
 

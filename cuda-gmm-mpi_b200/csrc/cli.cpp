@@ -12,6 +12,10 @@
 //   GMM_PRINT   1 = ENABLE_PRINT messages, default 0
 //   GMM_PATH    0 auto, 1 SIMT kernels, 2 tcgen05 kernels
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <chrono>
@@ -92,10 +96,21 @@ extern "C" int gmm_main(int argc, char** argv) {
     const int print = env_int("GMM_PRINT", 0);
     int D = 0, N = 0;
     if (print) std::printf("Parsing input file...");
-    float* events = gmm_read_data(argv[2], &D, &N);
-    if (!events) {
+    // "*.bin" (readData.cpp:28): only the header is read here; every GPU thread streams its own rows from the file to its
+    // device through pinned staging buffers (gmm_upload_events_file) and the .results writer maps the file — the host
+    // never allocates the data set.  Anything else (CSV) is parsed into host memory as in the reference.
+    const size_t plen = std::strlen(argv[2]);
+    const bool is_bin = plen >= 3 && std::strcmp(argv[2] + plen - 3, "bin") == 0;
+    float* events = nullptr;
+    if (is_bin) {
+        if (gmm_read_bin_header(argv[2], &D, &N)) { D = 0; N = 0; }
+    } else {
+        events = gmm_read_data(argv[2], &D, &N);
+    }
+    if ((!is_bin && !events) || D <= 0 || N <= 0) {
         std::printf("Error parsing input file. This could be due to an empty file ");
         std::printf("or an inconsistent number of dimensions. Aborting.\n");
+        gmm_free(events);
         return 1;
     }
     if (D > GMM_MAX_DIMENSIONS) { std::printf("ERROR: at most %d dimensions are supported.\n", GMM_MAX_DIMENSIONS); gmm_free(events); return 1; }
@@ -137,7 +152,8 @@ extern "C" int gmm_main(int argc, char** argv) {
         long long begin, count;
         gmm_shard_range(N, G, g, &begin, &count);
         gmm_ctx* ctx = nullptr;
-        int rc = gmm_create(&ctx, g, (int)count, D, K0, events + (size_t)begin * D, N, begin);
+        int rc = gmm_create(&ctx, g, (int)count, D, K0, events ? events + (size_t)begin * D : nullptr, N, begin);
+        if (!rc && is_bin) rc = gmm_upload_events_file(ctx, argv[2]);
         if (!rc) rc = gmm_set_option(ctx, "path", path);
         if (!rc) rc = gmm_set_option(ctx, "verbose", print);
         if (rc) { errs[g] = gmm_last_error(); setup_failed.store(1); }
@@ -202,7 +218,24 @@ extern "C" int gmm_main(int argc, char** argv) {
         gmm_free(events);
         return -1;
     }
-    if (want_output) gmm_write_results(results.c_str(), events, N, D, &saved.c, ideal_K);
+    if (want_output) {
+        const float* ev = events;
+        void* map = MAP_FAILED;
+        size_t map_len = 0;
+        if (is_bin) {                                   // the event columns of the .results file come straight from the mapped input
+            const int fd = open(argv[2], O_RDONLY);
+            struct stat st;
+            if (fd >= 0 && fstat(fd, &st) == 0 && (size_t)st.st_size >= 8 + sizeof(float) * (size_t)N * D) {
+                map_len = (size_t)st.st_size;
+                map = mmap(nullptr, map_len, PROT_READ, MAP_PRIVATE, fd, 0);
+            }
+            if (fd >= 0) close(fd);
+            if (map == MAP_FAILED) { std::printf("ERROR: Unable to map '%s'.\n", argv[2]); return -1; }
+            ev = reinterpret_cast<const float*>(static_cast<const char*>(map) + 8);
+        }
+        gmm_write_results(results.c_str(), ev, N, D, &saved.c, ideal_K);
+        if (map != MAP_FAILED) munmap(map, map_len);
+    }
     gmm_free(events);
     const auto t_end = std::chrono::steady_clock::now();
     auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };

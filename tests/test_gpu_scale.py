@@ -185,3 +185,30 @@ def test_full_size_config3_one_estep_one_mstep(loaded, oracle64):
     oracle64.mstep(soa, ref, K)
     oracle64.constants(ref, K)
     assert_params_close(got, ref, K)
+
+
+def test_upload_events_file_equals_array(loaded, tmp_path):
+    """gmm_upload_events_file streams this shard's rows of a .bin file (readData.cpp:35-47 format) to the device through
+    pinned staging buffers: bit-identical results to a context created from the host array, for a shard in the middle of
+    the file; a header that does not match the context is refused."""
+    pkg = loaded
+    N, D, K = 50_001, 16, 5
+    ev = pkg.synth.make_blobs(N, D, K, seed=91)
+    path = str(tmp_path / "ev.bin")
+    pkg.synth.write_bin(path, ev)
+    b, n = 10_007, 30_000
+    with pkg.Engine(np.ascontiguousarray(ev[b:b + n]), K, n_global=N, offset=b) as eng:
+        eng.seed(K)
+        ll_a, _ = eng.em(K, 3, 3)
+        a = eng.get_clusters(K, with_memberships=True)
+    with pkg.Engine(None, K, n_global=N, offset=b, n_local=n, D=D) as eng:
+        eng.upload_events_file(path)
+        eng.seed(K)
+        ll_b, _ = eng.em(K, 3, 3)
+        c = eng.get_clusters(K, with_memberships=True)
+    assert ll_a == ll_b
+    for f in ("N", "means", "R", "Rinv", "constant", "pi", "memberships"):
+        np.testing.assert_array_equal(getattr(a, f), getattr(c, f))
+    with pkg.Engine(None, K, n_global=N + 1, offset=0, n_local=n, D=D) as eng:
+        with pytest.raises(pkg.GmmError):
+            eng.upload_events_file(path)
