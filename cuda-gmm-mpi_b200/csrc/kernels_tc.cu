@@ -92,10 +92,26 @@ constexpr int kPhiBits = 11;     // |ph| <= 2^11 quanta
 constexpr float kGammaScale = 1024.0f;               // responsibilities are scaled by 2^10 in the operand
 constexpr float kGammaMagic = 1.5f * 134217728.0f;   // 1.5 * 2^27: ulp = 16 = 2^-6 in the scaled units
 
+// Row layout of the feature operand.  The four warps of a builder warpgroup run ONE instruction stream (round 1 / early
+// round 2 unrolled a different quarter of the feature list per warp: 50 KB of SASS against a 32 KB L1.5 instruction cache,
+// a third of the builders' stall samples were instruction fetch): warp p loads the event's coordinates ROTATED by p*D/4
+// dimensions (a run-time shared-memory address) and evaluates the same canonical list of RPP rows on them —
+//     r = 0                      1
+//     r = 1 + a          (a < S) z'_a
+//     r = 1 + S + a      (a < S) z'_a^2
+//     r = 1 + 2S + a*D/2 + (d-1) (a < S, 1 <= d <= D/2)   z'_a * z'_{(a+d) mod D}
+// with z'_t = z_{(t + pS) mod D}, S = D/4.  The rotations of the canonical pairs cover every unordered pair of
+// dimensions once, except the D/2 antipodal pairs (d = D/2), which two warps produce (one copy is ignored), and the
+// constant row (kept from warp 0).  Warp p writes operand rows [p*CPP*8, p*CPP*8 + RPP); tc_row_map() gives the packed
+// statistic each row feeds.
 template <int D> struct MCfg {
+    static_assert(D % 4 == 0, "tensor M-step: D must be a multiple of 4");
     static constexpr int F = 1 + D + D * (D + 1) / 2;
-    static constexpr int NCHUNK = (F + 7) / 8;            // 16-byte feature chunks actually written
-    static constexpr int MT = (F + 127) / 128;            // M tiles of 128 feature rows
+    static constexpr int S = D / 4;                       // rotation step between the four builder warps
+    static constexpr int RPP = 1 + 2 * S + S * (D / 2);   // canonical rows per warp
+    static constexpr int CPP = (RPP + 7) / 8;             // 16-byte chunks per warp
+    static constexpr int NCHUNK = 4 * CPP;                // chunks written per event
+    static constexpr int MT = (NCHUNK * 8 + 127) / 128;   // M tiles of 128 feature rows
     static constexpr int PHI_PART = MT * 128 * kTE * 2;   // bytes of one part (leading or remainder)
     static constexpr int PHI_STAGE = 2 * PHI_PART;
     static constexpr int G_PART = kNCL * kTE * 2;
@@ -113,9 +129,10 @@ template <int D> struct MCfg {
     static_assert(MT <= 3, "accumulator tiles");
 };
 
-// Rounding constants of the feature rows (kernel parameter: read as constant-bank operands, the row index is
-// static after unrolling): magic[f] = 1.5 * 2^23 * q_f, so that (v + magic) - magic = q_f * round(v / q_f).
-template <int D> struct MMagic { float m[MCfg<D>::NCHUNK * 8]; };
+// Rounding constants: (v + magic) - magic = q * round(v / q) with magic = 1.5 * 2^23 * q.  One quantum for the
+// coordinate rows and one for the product rows (bound = the largest |z_d| of the data over ALL dimensions, rounded up
+// to a power of two: after the standardisation the dimensions have the same scale).
+struct MMagic { float lin, prod; };
 
 __host__ __device__ constexpr int tri_row(int t) {        // t = i(i+1)/2 + j, j <= i  ->  i
     int i = 0;
@@ -129,43 +146,63 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 
-// Leading part / remainder of feature f of the centred/scaled event z (f is a compile-time constant after
-// unrolling).  Second moments: both parts come from the EXACT product (fused multiply-adds), rounded once each.
+// Leading part / remainder of canonical row r for the (rotated) event z (r is a compile-time constant after
+// unrolling).  Products: both parts come from the EXACT product (fused multiply-adds), rounded once each.
 template <int D>
-__device__ __forceinline__ void feature_split(const float (&z)[D], int f, float magic, float& h, float& l) {
-    constexpr int F = MCfg<D>::F;
-    if (f == 0) { h = 1.0f; l = 0.0f; }
-    else if (f <= D) {
-        const float v = z[f - 1];
-        h = __fsub_rn(__fadd_rn(v, magic), magic);
+__device__ __forceinline__ void feature_split(const float (&z)[D], int r, const MMagic& mg, float& h, float& l) {
+    using C = MCfg<D>;
+    if (r == 0) { h = 1.0f; l = 0.0f; }
+    else if (r <= C::S) {
+        const float v = z[r - 1];
+        h = __fsub_rn(__fadd_rn(v, mg.lin), mg.lin);
         l = __fsub_rn(v, h);
-    } else if (f < F) {
-        const int t = f - 1 - D;
-        const int i = tri_row(t);
-        const int j = t - i * (i + 1) / 2;
-        h = __fsub_rn(__fmaf_rn(z[i], z[j], magic), magic);
-        l = __fmaf_rn(z[i], z[j], -h);
+    } else if (r < C::RPP) {
+        int a, b;
+        if (r <= 2 * C::S) { a = r - 1 - C::S; b = a; }
+        else { const int t = r - 1 - 2 * C::S; a = t / (D / 2); b = (a + 1 + t % (D / 2)) % D; }
+        h = __fsub_rn(__fmaf_rn(z[a], z[b], mg.prod), mg.prod);
+        l = __fmaf_rn(z[a], z[b], -h);
     } else { h = 0.0f; l = 0.0f; }
 }
 
-// Builds the 16-byte chunks c = P, P+4, P+8, ... of the feature vector of one event and
-// stores both parts into the MN-major operand image:
-//   byte(f, e) = (f/8)*512 + (e/8)*128 + (e%8)*16 + (f%8)*2        (LBO = 128, SBO = 512)
-template <int D, int P>
-__device__ __forceinline__ void build_phi_chunks(const float (&z)[D], const MMagic<D>& mg, uint8_t* hi_base, uint8_t* lo_base, int e) {
-    constexpr int NCHUNK = MCfg<D>::NCHUNK;
-    const int eoff = (e >> 3) * 128 + (e & 7) * 16;
+// Builds the CPP 16-byte chunks of one event for builder warp `part` and stores both parts into the MN-major operand image:
+//   byte(row, e) = (row/8)*512 + (e/8)*128 + (e%8)*16 + (row%8)*2        (LBO = 128, SBO = 512)
+template <int D>
+__device__ __forceinline__ void build_phi_chunks(const float (&z)[D], const MMagic& mg, uint8_t* hi_base, uint8_t* lo_base, int e, int part) {
+    using C = MCfg<D>;
+    const int eoff = part * (C::CPP * 512) + (e >> 3) * 128 + (e & 7) * 16;
 #pragma unroll
-    for (int c = P; c < NCHUNK; c += 4) {
+    for (int c = 0; c < C::CPP; c++) {
         float hi[8], lo[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) feature_split<D>(z, c * 8 + u, mg.m[c * 8 + u], hi[u], lo[u]);
+        for (int u = 0; u < 8; u++) feature_split<D>(z, c * 8 + u, mg, hi[u], lo[u]);
         uint4 h, l;
         h.x = pack_half2(hi[0], hi[1]); h.y = pack_half2(hi[2], hi[3]); h.z = pack_half2(hi[4], hi[5]); h.w = pack_half2(hi[6], hi[7]);   // exact: <= 2048 quanta
         l.x = pack_half2(lo[0], lo[1]); l.y = pack_half2(lo[2], lo[3]); l.z = pack_half2(lo[4], lo[5]); l.w = pack_half2(lo[6], lo[7]);
         *reinterpret_cast<uint4*>(hi_base + c * 512 + eoff) = h;
         *reinterpret_cast<uint4*>(lo_base + c * 512 + eoff) = l;
     }
+}
+
+// Packed statistic (index into a cluster's F values, -1 = ignored copy) and the two dimensions (-1 = none) behind
+// operand row `row`; host side of the layout above.
+struct RowInfo { int f, i, j; };
+static RowInfo tc_row_info(int D, int row) {
+    const int S = D / 4, RPP = 1 + 2 * S + S * (D / 2), CPP = (RPP + 7) / 8;
+    const int p = row / (CPP * 8), r = row % (CPP * 8);
+    RowInfo o{-1, -1, -1};
+    if (p >= 4 || r >= RPP) return o;
+    if (r == 0) { if (p == 0) o.f = 0; return o; }
+    if (r <= S) { o.i = (r - 1 + p * S) % D; o.f = 1 + o.i; return o; }
+    int a, b;
+    if (r <= 2 * S) { a = r - 1 - S; b = a; }
+    else { const int t = r - 1 - 2 * S; a = t / (D / 2); b = (a + 1 + t % (D / 2)) % D; }
+    const int ta = (a + p * S) % D, tb = (b + p * S) % D;
+    if (a != b && (b - a + D) % D == D / 2 && ta >= D / 2) return o;       // antipodal pair: the copy with the smaller first index counts
+    o.i = ta > tb ? ta : tb;
+    o.j = ta > tb ? tb : ta;
+    o.f = feat2(D, o.i, o.j);
+    return o;
 }
 
 // Feature tile `mt` is drained after sub-tile i when its 128-event chain ends there: the chains of the tiles are
@@ -179,7 +216,7 @@ __device__ __forceinline__ bool chain2_starts(int i, int mt) { return i == 0 || 
 template <int D>
 __global__ void __launch_bounds__(kMThreads, 1)
 mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g, int n,
-                float* __restrict__ scratch, int events_per_cta, const __grid_constant__ MMagic<D> magic) {
+                float* __restrict__ scratch, int events_per_cta, const __grid_constant__ MMagic magic) {
     using C = MCfg<D>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -284,11 +321,12 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             const int os = i % kNST, oph = (i / kNST) & 1;
             mbar_wait_parked(&raw_full[rs], rph, 200);
             // --- features of event `lane` ---
-            float z[D];                                // already centred and scaled (tc_set_shift_scale writes the z copy)
+            float z[D];                                // already centred and scaled (tc_set_shift_scale writes the z copy), rotated by part * S
             {
                 const float* xr = reinterpret_cast<const float*>(smem + C::OFF_RAWX + rs * C::RAWX) + lane;   // [d][32]: conflict-free
+                int dd = part * C::S;
 #pragma unroll
-                for (int d = 0; d < D; d++) z[d] = xr[d * kTE];
+                for (int d = 0; d < D; d++) { z[d] = xr[dd * kTE]; dd = dd + 1 == D ? 0 : dd + 1; }
             }
             // --- responsibilities: thread -> (cluster row k, 8-event chunk ce), two items per thread.
             // The raw tile is written by TMA with SWIZZLE_128B (16-byte chunk c of row r sits at chunk
@@ -333,12 +371,7 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             mbar_wait_parked(&op_empty[os], oph ^ 1, 200);
             uint8_t* phi_hi = smem + C::OFF_PHI + os * C::PHI_STAGE;
             uint8_t* phi_lo = phi_hi + C::PHI_PART;
-            switch (part) {
-                case 0: build_phi_chunks<D, 0>(z, magic, phi_hi, phi_lo, lane); break;
-                case 1: build_phi_chunks<D, 1>(z, magic, phi_hi, phi_lo, lane); break;
-                case 2: build_phi_chunks<D, 2>(z, magic, phi_hi, phi_lo, lane); break;
-                default: build_phi_chunks<D, 3>(z, magic, phi_hi, phi_lo, lane); break;
-            }
+            build_phi_chunks<D>(z, magic, phi_hi, phi_lo, lane, part);
             {
                 // K-major B image: byte(k, e) = (k/8)*512 + (e/8)*128 + (k%8)*16 + (e%8)*2      (LBO = 128, SBO = 512); gl = rows 64..127
                 uint8_t* g_hi = smem + C::OFF_G + os * C::G_STAGE;
@@ -371,19 +404,15 @@ mstep_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 full ^= 1u << mt;
                 tc_fence_after();
                 const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + mt * 128;
+                // group 0: exact leading products; group 1 (only when its longer chain ends here): remainder products.
+                // One copy of the code for both (not unrolled: the kernel's SASS has to stay inside the 32 KB L1.5 I-cache).
+                const int ngroups = chain2_ends(i, mt, nsub) ? 2 : 1;
+#pragma unroll 1
+                for (int grp = 0; grp < ngroups; grp++) {
 #pragma unroll
-                for (int b = 0; b < kNCL / 32; b++) {              // exact leading products
-                    uint32_t a[32];
-                    tmem_ld_32x32(tbase + b * 32, a);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; j++) racc[mt * kNCL + b * 32 + j] += __uint_as_float(a[j]);
-                }
-                if (chain2_ends(i, mt, nsub)) {
-#pragma unroll
-                    for (int b = 0; b < kNCL / 32; b++) {          // remainder products
+                    for (int b = 0; b < kNCL / 32; b++) {
                         uint32_t a[32];
-                        tmem_ld_32x32(tbase + kNCL + b * 32, a);
+                        tmem_ld_32x32(tbase + grp * kNCL + b * 32, a);
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 32; j++) racc[mt * kNCL + b * 32 + j] += __uint_as_float(a[j]);
@@ -422,20 +451,19 @@ __global__ void standardise_soa_kernel(const float* __restrict__ xs, float* __re
 }
 
 // Reduce the per-CTA FP32 partials in double, undo the operand scaling and write the packed statistics.
+// rowmap[row] = (packed statistic index or -1, dimension i, dimension j) of operand row `row` (tc_row_info).
 __global__ void __launch_bounds__(256)
-mstep_tc_finalize_kernel(const float* __restrict__ scratch, int ncta_x, int MT, int K, int D, int F,
+mstep_tc_finalize_kernel(const float* __restrict__ scratch, int ncta_x, int MT, int K, int F, const int3* __restrict__ rowmap,
                          const double* __restrict__ scale, double* __restrict__ stats) {
-    // one block per feature row f; thread -> (cluster column, quarter of the CTAs): 256-byte coalesced reads
+    // one block per operand row; thread -> (cluster column, quarter of the CTAs): 256-byte coalesced reads
     __shared__ double part[4][kNCL];
-    const int f = blockIdx.x, mt = f / 128, row = f % 128;
+    const int3 rm = rowmap[blockIdx.x];
+    if (rm.x < 0) return;
+    const int mt = blockIdx.x / 128, row = blockIdx.x % 128;
     const int col = threadIdx.x & (kNCL - 1), q = threadIdx.x / kNCL;
     double fac = 1.0 / (double)kGammaScale;
-    if (f >= 1 && f <= D) fac *= scale[f - 1];
-    else if (f > D) {
-        const int t = f - 1 - D;
-        const int i = tri_row(t), j = t - i * (i + 1) / 2;
-        fac *= scale[i] * scale[j];
-    }
+    if (rm.y >= 0) fac *= scale[rm.y];
+    if (rm.z >= 0) fac *= scale[rm.z];
     for (int ty = 0; ty * kNCL < K; ty++) {
         double s = 0;
         for (int cx = q; cx < ncta_x; cx += 4)
@@ -443,11 +471,10 @@ mstep_tc_finalize_kernel(const float* __restrict__ scratch, int ncta_x, int MT, 
         part[q][col] = s;
         __syncthreads();
         const int k = ty * kNCL + col;
-        if (q == 0 && k < K) stats[(size_t)k * F + f] += (part[0][col] + part[1][col] + part[2][col] + part[3][col]) * fac;
+        if (q == 0 && k < K) stats[(size_t)k * F + rm.x] += (part[0][col] + part[1][col] + part[2][col] + part[3][col]) * fac;
         __syncthreads();
     }
 }
-
 
 // ===========================================================================
 // E-step (estep1 + estep2 of the reference, gaussian_kernel.cu:383-512) on
@@ -466,36 +493,28 @@ mstep_tc_finalize_kernel(const float* __restrict__ scratch, int ncta_x, int MT, 
 // (all clusters: 172 KB at K=64, D=24) RESIDENT in the shared memory of one CTA;
 // only the event tiles stream.
 //
-// One persistent CTA per SM, 512 threads:
-//   warp 1      MMA issuer: per 128-event tile, per supergroup of 16 clusters and per block c of 8
-//               output dimensions, the k-steps that block needs (tcgen05.mma M=128, N=128, K=16)
-//   warp 2      TMEM allocation (4 accumulator buffers x 128 columns)
-//   warps 4-7   converters: coalesced loads of the event rows, centre/scale, FP16 hi/lo
-//               split, K-major SWIZZLE_NONE operand image (2 stages)
-//   warps 8-15  epilogue (two warpgroups, each takes 8 of the 16 clusters of every supergroup):
-//               tcgen05.ld -> packed squares, carried over the blocks -> base-2 logits ->
-//               max / sum-exp2 (+ exchange between the warpgroups) -> responsibilities
-//               (coalesced 128-byte row segments) + log-likelihood (double)
+// One persistent CTA per SM, 768 threads in six warpgroups (round 2: the epilogue is split in two stages — round 1's
+// eight epilogue warps did squares, log-sum-exp and stores back to back, 6370 cycles per 128-event tile of which the MMA
+// issuer was stalled 3500 behind full accumulators while they were busy with log-sum-exp and stores; the per-phase
+// counters of that kernel are in profiles/):
+//   warp 1       MMA issuer: per 128-event tile, per supergroup of 16 clusters and per block c of 8
+//                output dimensions, the k-steps that block needs (tcgen05.mma M=128, N=128, K=16)
+//   warp 2       TMEM allocation: 3 accumulator buffers x 128 columns + 2 x 64 columns for the hand-over of q
+//   warps 4-7    converters: coalesced loads of the event rows, centre/scale, FP16 hi/lo
+//                split, K-major SWIZZLE_NONE operand image (2 stages)
+//   warps 8-15   squares (two warpgroups, each takes 8 of the 16 clusters of every supergroup): tcgen05.ld of the
+//                accumulators (buffer released as soon as the values are in registers) -> packed fma.f32x2 sums of
+//                squares carried over the blocks -> q[event][cluster] written back to TMEM (tcgen05.st)
+//   warps 16-23  log-sum-exp + stores (two warpgroups, 32 clusters each): tcgen05.ld of q -> base-2 logits ->
+//                max / sum-exp2 (+ exchange between the warpgroups) -> responsibilities (coalesced 128-byte row
+//                segments) + log-likelihood (double) — for tile t while the MMAs and the squares of tile t+1 run
 // ===========================================================================
-
-// GMM_ESTEP_PROF=1 (build-time, diagnostic variant only): the epilogue of CTA 0 / warp 8 accumulates clock64() spans of its
-// phases and prints them at the end of the kernel — where do the cycles of a tile go (waiting for accumulators, tcgen05.ld,
-// squares, logits + log-sum-exp + exchange, stores)?  Off by default: no code is generated.
-#ifndef GMM_ESTEP_PROF
-#define GMM_ESTEP_PROF 0
-#endif
-#if GMM_ESTEP_PROF
-#define EPROF(stmt) stmt
-#else
-#define EPROF(stmt)
-#endif
 
 // Block structure.  W is upper triangular, so the 8 output columns d in [8c, 8c+8) of a cluster
 // ("block" c) only need the K chunks z_j with j >= c.  Columns are therefore grouped by block:
 // one MMA N tile = block c of 16 clusters (N = 128), and block c issues only the k-steps it needs —
 // 5 + 4 + 2 = 11 instead of 15 at D = 24 (-27 % tensor work and TMEM accumulator traffic).
 template <int D> struct ECfg {
-    static constexpr int NWG = 2;                             // epilogue warpgroups
     static_assert(D % 8 == 0, "tensor E-step: D must be a multiple of 8");
     static constexpr int CP = D / 8;                          // 8-wide chunks of z / blocks of output columns
     static constexpr int NLO = (CP + 1 + 1) / 2 * 2;          // chunks of the [zh | ones (| pad)] x [Wl | v] part
@@ -504,9 +523,11 @@ template <int D> struct ECfg {
     static constexpr int GB = 16;                             // clusters per supergroup
     static constexpr int N = GB * 8;                          // MMA N = one block of a supergroup (128 columns)
     static constexpr int MAXSG = 64 / GB;                     // up to 64 clusters resident
-    static constexpr int NBUF = 512 / N;                      // TMEM accumulator buffers (4)
-    static constexpr int CW = GB / NWG;                       // clusters per epilogue warpgroup per supergroup
-    static constexpr int LPT = MAXSG * CW;                    // logits held per epilogue thread (32)
+    static constexpr int NBUF = 3;                            // TMEM accumulator buffers (3 x 128 columns)
+    static constexpr int QCOL = NBUF * N;                     // first column of the q hand-over: 2 tiles x 64 clusters
+    static constexpr int NWG = 2;                             // warpgroups per epilogue stage
+    static constexpr int CW = GB / NWG;                       // clusters per warpgroup per supergroup
+    static constexpr int LPT = MAXSG * CW;                    // logits held per log-sum-exp thread (32)
     static constexpr int A_STAGE = NCHKA * 128 * 16;
     static constexpr int B_BLOCK = NCHKB * N * 16;            // one block of one supergroup
     static constexpr int B_SG = CP * B_BLOCK;
@@ -516,14 +537,12 @@ template <int D> struct ECfg {
     static constexpr int OFF_EX = OFF_CK + 512;               // exchange: [2 parity][NWG][128] x (max, sum)
     static constexpr int OFF_BAR = OFF_EX + 2 * NWG * 128 * 8;
     static constexpr int SMEM_BYTES = OFF_BAR + 512;
-    static constexpr int THREADS = 256 + 128 * NWG;           // warpgroup 0, converters, NWG epilogue warpgroups
+    static constexpr int THREADS = 256 + 2 * 128 * NWG;       // warpgroup 0, converters, 2 square + 2 log-sum-exp warpgroups
+    static_assert(QCOL + 2 * 64 <= 512, "TMEM columns");
 };
 
-// Both epilogue warpgroups work on every tile: each takes 8 of the 16 clusters of a supergroup and they exchange
-// (max, sum) through shared memory.  (Round 1 also carried an alternate-tile variant and a four-warpgroup variant;
-// both were measured — 1.73 ms and 1.85 ms per 4M events x 2.5 against 1.67 — and removed.)
 template <int D>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(768, 1)
 estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_img, const float* __restrict__ ck,
                 const float* __restrict__ shift_f, const float* __restrict__ inv_scale_f, float* __restrict__ memb,
                 size_t pitch, int n, int K, int NSG, double* __restrict__ ll_out, float* __restrict__ den_out) {
@@ -538,8 +557,10 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
     uint64_t* a_empty = bars + 2;       // [2]  tcgen05.commit
     uint64_t* b_full = bars + 4;        // [1]
     uint64_t* acc_full = bars + 5;      // [NBUF]  tcgen05.commit
-    uint64_t* acc_empty = bars + 5 + C::NBUF;     // [NBUF]  8 epilogue warps
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * C::NBUF);
+    uint64_t* acc_empty = bars + 8;     // [NBUF]  8 square warps
+    uint64_t* q_full = bars + 11;       // [2]  8 square warps: q of a tile is in TMEM
+    uint64_t* q_empty = bars + 13;      // [2]  8 log-sum-exp warps: q of a tile is in their registers
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
     float2* ck_s = reinterpret_cast<float2*>(smem + C::OFF_CK);
     float2* ex = reinterpret_cast<float2*>(smem + C::OFF_EX);
     float* sh_s = reinterpret_cast<float*>(smem + C::OFF_BAR + 128);   // [32] shift, [32] inverse scale
@@ -552,6 +573,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; s++) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < C::NBUF; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4 * NWG); }
+        for (int s = 0; s < 2; s++) { mbar_init(&q_full[s], 4 * NWG); mbar_init(&q_empty[s], 4 * NWG); }
         mbar_init(b_full, 1);
         fence_mbar_init();
     }
@@ -571,9 +593,9 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    // register re-partition inside the CTA's launch allocation (512 x 128): WG0 40, converters 72, epilogue 2 x 200
+    // register pools (launch: 768 x 80 = 61440): WG0 24, converters 72, squares 2 x 112, log-sum-exp 2 x 80
     if (warp < 4) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
       if (warp == 1) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
@@ -584,7 +606,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                 mbar_wait_parked(&a_full[as], aph, 200);
                 tc_fence_after();
                 const uint32_t abase = smem_u32(smem + C::OFF_A + as * C::A_STAGE);
-                uint32_t buf = 0;                              // the buffer sequence restarts with every tile (epilogue: same rule)
+                uint32_t buf = 0;                              // the buffer sequence restarts with every tile (squares: same rule)
                 for (int sg = 0; sg < NSG; sg++) {
 #pragma unroll
                     for (int c = 0; c < C::CP; c++) {
@@ -663,45 +685,37 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[st]);
         }
-    } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
-        // ===================== epilogue =====================
-        const int wg = (warp - 8) >> 2, q = warp & 3;
-        const int row = q * 32 + lane;
-        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        double ll_acc = 0.0;
-        EPROF(long long pr_wait = 0; long long pr_ld = 0; long long pr_sq = 0; long long pr_lse = 0; long long pr_st = 0; long long pr_t0 = clock64();)
-        uint32_t pf[C::NBUF];                                  // wait parity of acc_full[b]; b is static after unrolling
-#pragma unroll
-        for (int b = 0; b < C::NBUF; b++) pf[b] = 0u;
-        constexpr float kLn2 = 0.6931471805599453f;
+    } else if (warp < 16) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        // ===================== squares: accumulators -> q[event][cluster] (TMEM) =====================
+        const int sq = (warp - 8) >> 2, qd = warp & 3;
+        const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+        uint32_t pf = 0u;                                      // wait parity of acc_full[b], one bit per buffer
         for (int it = 0; it < my_tiles; it++) {
-            const long long e = (long long)((int)blockIdx.x + it * (int)gridDim.x) * 128 + row;
-            float lg[C::LPT];                                  // logits in base 2 (ck_s is pre-multiplied by log2 e)
-            float mx = -INFINITY;
-#pragma unroll
-            for (int sg = 0; sg < C::MAXSG; sg++) {
-                if (sg < NSG) {
+            const int tb = it & 1;
+            mbar_wait_parked(&q_empty[tb], ((it >> 1) & 1) ^ 1, 200);      // the previous tile in this q buffer has been read
+            tc_fence_after();
+            uint32_t buf = 0;                                  // the buffer sequence restarts with every tile (MMA issuer: same rule)
+#pragma unroll 1
+            for (int sg = 0; sg < NSG; sg++) {                 // not unrolled: the kernel's SASS has to stay inside the 32 KB L1.5 I-cache
+                {
                     uint64_t qa[C::CW], qb[C::CW];             // packed partial sums of squares of this warpgroup's 8 clusters
 #pragma unroll
                     for (int i = 0; i < C::CW; i++) { qa[i] = 0ull; qb[i] = 0ull; }
 #pragma unroll
                     for (int c = 0; c < C::CP; c++) {
-                        const int buf = (sg * C::CP + c) % C::NBUF;   // compile-time: the sequence restarts with every tile
-                        EPROF(const long long p0 = clock64();)
-                        mbar_wait_parked(&acc_full[buf], pf[buf], 200);
-                        pf[buf] ^= 1u;
+                        mbar_wait_parked(&acc_full[buf], (pf >> buf) & 1u, 200);
+                        pf ^= 1u << buf;
                         tc_fence_after();
-                        EPROF(const long long p1 = clock64(); pr_wait += p1 - p0;)
-                        const uint32_t tcol = tmem + lane_base + buf * C::N + wg * (C::CW * 8);
+                        const uint32_t tcol = tmem + lane_base + buf * C::N + sq * (C::CW * 8);
                         uint32_t v[C::CW * 8];                 // CW clusters x 8 columns
                         tmem_ld_32x32(tcol, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
                         tmem_ld_32x32(tcol + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
                         tmem_ld_wait();
-                        EPROF(const long long p2 = clock64(); pr_ld += p2 - p1;)
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&acc_empty[buf]);   // the block is in registers: hand the buffer back
+                        buf = buf + 1 == C::NBUF ? 0 : buf + 1;
 #pragma unroll
                         for (int i = 0; i < C::CW; i++) {
                             sq_acc2(qa[i], v[i * 8 + 0], v[i * 8 + 1]);
@@ -709,22 +723,49 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                             sq_acc2(qa[i], v[i * 8 + 4], v[i * 8 + 5]);
                             sq_acc2(qb[i], v[i * 8 + 6], v[i * 8 + 7]);
                         }
-                        EPROF(asm volatile("" : "+l"(qa[0])); pr_sq += clock64() - p2;)
                     }
+                    uint32_t qv[C::CW];
 #pragma unroll
-                    for (int i = 0; i < C::CW; i++) {
-                        const float2 cm = ck_s[sg * C::GB + wg * C::CW + i];
-                        const float l = fmaf(cm.y, hsum2(qa[i], qb[i]), cm.x);
-                        lg[sg * C::CW + i] = l;
-                        mx = fmaxf(mx, l);
-                    }
-                } else {
+                    for (int i = 0; i < C::CW; i++) qv[i] = __float_as_uint(hsum2(qa[i], qb[i]));
+                    // column of cluster (sg, sq, i) in the hand-over: tile buffer tb, warpgroup sq, then sg * 8 + i
+                    tmem_st_32x8(tmem + lane_base + C::QCOL + tb * 64 + sq * (C::MAXSG * C::CW) + sg * C::CW, qv);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&q_full[tb]);
+        }
+    } else {
+        // ===================== log-sum-exp + stores (80 registers: the launch allocation) =====================
+        const int wg = (warp - 16) >> 2, qd = warp & 3;
+        const int row = qd * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+        double ll_acc = 0.0;
+        constexpr float kLn2 = 0.6931471805599453f;
+        for (int it = 0; it < my_tiles; it++) {
+            const int tb = it & 1;
+            const long long e = (long long)((int)blockIdx.x + it * (int)gridDim.x) * 128 + row;
+            float lg[C::LPT];                                  // q, then logits in base 2 (ck_s is pre-multiplied by log2 e)
+            mbar_wait_parked(&q_full[tb], (it >> 1) & 1, 200);
+            tc_fence_after();
+            tmem_ld_32x32(tmem + lane_base + C::QCOL + tb * 64 + wg * C::LPT, *reinterpret_cast<uint32_t(*)[32]>(&lg[0]));
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&q_empty[tb]);
+            float mx = -INFINITY;
 #pragma unroll
-                    for (int i = 0; i < C::CW; i++) lg[sg * C::CW + i] = -INFINITY;
+            for (int sg = 0; sg < C::MAXSG; sg++) {
+#pragma unroll
+                for (int i = 0; i < C::CW; i++) {
+                    const float2 cm = ck_s[sg * C::GB + wg * C::CW + i];
+                    const float l = sg < NSG ? fmaf(cm.y, lg[sg * C::CW + i], cm.x) : -INFINITY;   // columns of unused supergroups are not written
+                    lg[sg * C::CW + i] = l;
+                    mx = fmaxf(mx, l);
                 }
             }
             // log-sum-exp over the clusters (estep2, gaussian_kernel.cu:481-503): local part, then the two warpgroups combine
-            EPROF(const long long p3 = clock64();)
             float sm = 0.f;
 #pragma unroll
             for (int j = 0; j < C::LPT; j++) { lg[j] = ex2_approx(lg[j] - mx); sm += lg[j]; }
@@ -737,7 +778,6 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
             const float S = sm * own + o.y * ex2_approx(o.x - M);
             const float denom = fmaf(M, kLn2, logf(S));              // :490-494, back in natural units
             const float scale = own / S;                             // exp(l - denom) = 2^(l2 - mx) * 2^(mx - M) / S
-            EPROF(const long long p4 = clock64(); pr_lse += p4 - p3;)
             if (e < n) {
                 if (wg == 0) {
                     if (den_out) den_out[e] = denom;
@@ -758,12 +798,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                     }
                 }
             }
-            EPROF(pr_st += clock64() - p4;)
         }
-        EPROF(if (blockIdx.x == 0 && warp == 8 && lane == 0)
-                  printf("estep epilogue profile (CTA 0, warp 8): %d tiles, cycles per tile: total %.0f = wait acc_full %.0f + tcgen05.ld %.0f + squares %.0f + "
-                         "lse/exchange %.0f + stores %.0f + rest\n", my_tiles, (double)(clock64() - pr_t0) / my_tiles, (double)pr_wait / my_tiles,
-                         (double)pr_ld / my_tiles, (double)pr_sq / my_tiles, (double)pr_lse / my_tiles, (double)pr_st / my_tiles);)
         if (wg == 0 && den_out == nullptr) {
             ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 16);
             ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 8);
@@ -840,7 +875,8 @@ struct TcState {
     bool have_shift = false;
     bool mstep_ready = false;        // the fixed-point quanta of the feature rows are set and inside the supported range
     float zmax[GMM_MAX_DIMENSIONS] = {0};    // power-of-two bound of |z_d| over the whole data set
-    float magic[41 * 8] = {0};       // rounding constants of the feature rows (MMagic)
+    MMagic magic{0.f, 0.f};          // rounding constants of the coordinate / product rows
+    int3* d_rowmap = nullptr;        // [MT * 128] operand row -> (packed statistic, dimension i, dimension j)
     // E-step
     CUtensorMap tm_x128{};
     bool emap_ok = false;
@@ -934,7 +970,23 @@ int tc_create(TcState** out, const float* d_x_aos, const float* d_x_soa, int n, 
         if (passes > 1) TC_CUDA_TRY(cudaMalloc(&t->d_den, sizeof(float) * (size_t)passes * memb_pitch));
         t->emap_ok = true;
     }
-    const int mt = (num_features(D) + 127) / 128;
+    const int rpp = 1 + 2 * (D / 4) + (D / 4) * (D / 2), nrows = 4 * ((rpp + 7) / 8) * 8;
+    const int mt = (nrows + 127) / 128;
+    {
+        std::vector<int3> rm((size_t)mt * 128);
+        std::vector<char> seen((size_t)num_features(D), 0);
+        for (int row = 0; row < mt * 128; row++) {
+            const RowInfo ri = tc_row_info(D, row);
+            rm[row] = make_int3(ri.f, ri.i, ri.j);
+            if (ri.f >= 0) {
+                if (seen[ri.f]) return fail(GMM_ERR_STATE, "tensor M-step row map: a statistic is produced twice");
+                seen[ri.f] = 1;
+            }
+        }
+        for (char c : seen) if (!c) return fail(GMM_ERR_STATE, "tensor M-step row map: a statistic is not produced");
+        TC_CUDA_TRY(cudaMalloc(&t->d_rowmap, sizeof(int3) * rm.size()));
+        TC_CUDA_TRY(cudaMemcpy(t->d_rowmap, rm.data(), sizeof(int3) * rm.size(), cudaMemcpyHostToDevice));
+    }
     const int ytiles = (Kmax + kNCL - 1) / kNCL;
     t->scratch_floats = (size_t)num_sms * ytiles * mt * 128 * kNCL;
     TC_CUDA_TRY(cudaMalloc(&t->d_scratch, sizeof(float) * t->scratch_floats));
@@ -953,7 +1005,7 @@ bool tc_estep_range_ok(const TcState* t) {
 void tc_destroy(TcState* t) {
     if (!t) return;
     cudaFree(t->d_shift_f); cudaFree(t->d_inv_scale_f); cudaFree(t->d_scale); cudaFree(t->d_scratch);
-    cudaFree(t->d_opnd); cudaFree(t->d_den); cudaFree(t->d_z_soa);
+    cudaFree(t->d_opnd); cudaFree(t->d_den); cudaFree(t->d_z_soa); cudaFree(t->d_rowmap);
     if (t->h_opnd) cudaFreeHost(t->h_opnd);
     if (t->ev_h2d) cudaEventDestroy(t->ev_h2d);
     delete t;
@@ -977,24 +1029,17 @@ int tc_set_shift_scale(TcState* t, double* shift, const double* scale, const dou
         if (za > 0 && std::isfinite(za)) { e2 = std::ilogb(za) + 1; }      // za < 2^e2
         t->zmax[d] = std::isfinite(za) ? (float)std::ldexp(1.0, e2) : INFINITY;
     }
-    // Fixed-point quanta of the M-step feature rows: q = bound * 2^-11, magic = 1.5 * 2^23 * q.  Data with outliers
-    // beyond 64 standard deviations would leave too few bits below the quantum for the bulk of the events: such a data
-    // set is served by the FP64 SIMT M-step instead (tc_mstep_ready() false; GMM_PATH_TENSOR reports it).
-    t->mstep_ready = true;
+    // Fixed-point quanta of the M-step feature rows: q = bound * 2^-11, magic = 1.5 * 2^23 * q, bound = the power-of-two
+    // bound of |z| over all dimensions (squared for the product rows).  Data with outliers beyond 64 standard deviations
+    // would leave too few bits below the quantum for the bulk of the events: such a data set is served by the FP64
+    // SIMT M-step instead (tc_mstep_ready() false; GMM_PATH_TENSOR reports it).
     {
-        const int D = t->D, F = num_features(D);
-        for (int f = 0; f < 41 * 8; f++) {
-            double bound = 1.0;
-            if (f >= 1 && f <= D) bound = t->zmax[f - 1];
-            else if (f > D && f < F) {
-                const int tt = f - 1 - D;
-                const int i = tri_row(tt), j = tt - i * (i + 1) / 2;
-                bound = (double)t->zmax[i] * (double)t->zmax[j];
-            }
-            t->magic[f] = (float)(1.5 * 8388608.0 * bound / (double)(1 << kPhiBits));
-        }
-        for (int d = 0; d < D; d++)
-            if (!(t->zmax[d] <= 64.0f)) t->mstep_ready = false;
+        float zb = 0.f;
+        for (int d = 0; d < t->D; d++) zb = std::fmax(zb, t->zmax[d]);
+        t->mstep_ready = zb <= 64.0f;                              // false for inf / nan too
+        const double q = (double)zb / (double)(1 << kPhiBits);
+        t->magic.lin = (float)(1.5 * 8388608.0 * q);
+        t->magic.prod = (float)(1.5 * 8388608.0 * q * (double)zb);
     }
     TC_CUDA_TRY(cudaMemcpyAsync(t->d_shift_f, sf, sizeof(sf), cudaMemcpyHostToDevice, stream));
     TC_CUDA_TRY(cudaMemcpyAsync(t->d_inv_scale_f, isf, sizeof(isf), cudaMemcpyHostToDevice, stream));
@@ -1235,7 +1280,6 @@ static int launch_mstep_d(TcState* t, int K, double* d_stats, cudaStream_t strea
     using C = MCfg<D>;
     static_assert(C::SMEM_BYTES <= 232448, "shared memory budget");
     static_assert(C::TMEM_COLS <= 512, "TMEM budget");
-    static_assert(sizeof(MMagic<D>) <= sizeof(TcState::magic), "magic table");
     if (!t->attr_mstep) {
         TC_CUDA_TRY(cudaFuncSetAttribute(mstep_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         t->attr_mstep = true;
@@ -1247,12 +1291,9 @@ static int launch_mstep_d(TcState* t, int K, double* d_stats, cudaStream_t strea
     const int gy = (K + kNCL - 1) / kNCL;
     if ((size_t)gx * gy * C::MT * 128 * kNCL > t->scratch_floats) return fail(GMM_ERR_STATE, "tensor M-step scratch too small");
     dim3 grid(gx, gy);
-    MMagic<D> mg;
-    std::memcpy(mg.m, t->magic, sizeof(mg.m));
-    mstep_tc_kernel<D><<<grid, kMThreads, C::SMEM_BYTES, stream>>>(t->tm_x, t->tm_g, t->n, t->d_scratch, per, mg);
+    mstep_tc_kernel<D><<<grid, kMThreads, C::SMEM_BYTES, stream>>>(t->tm_x, t->tm_g, t->n, t->d_scratch, per, t->magic);
     TC_CUDA_TRY(cudaGetLastError());
-    const int F = C::F;
-    mstep_tc_finalize_kernel<<<F, 256, 0, stream>>>(t->d_scratch, gx, C::MT, K, D, F, t->d_scale, d_stats);
+    mstep_tc_finalize_kernel<<<C::NCHUNK * 8, 256, 0, stream>>>(t->d_scratch, gx, C::MT, K, C::F, t->d_rowmap, t->d_scale, d_stats);
     TC_CUDA_TRY(cudaGetLastError());
     return GMM_OK;
 }
