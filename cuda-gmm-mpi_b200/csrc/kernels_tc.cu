@@ -545,10 +545,16 @@ template <int D>
 __global__ void __launch_bounds__(768, 1)
 estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_img, const float* __restrict__ ck,
                 const float* __restrict__ shift_f, const float* __restrict__ inv_scale_f, float* __restrict__ memb,
-                size_t pitch, int n, int K, int NSG, double* __restrict__ ll_out, float* __restrict__ den_out) {
-    // K / NSG / b_img / ck / memb describe ONE pass of at most 64 clusters.  With more than 64 clusters the host
-    // launches one pass per 64 (den_out != nullptr): each pass normalises within itself and records its
-    // log-denominator per event; estep_tc_combine_kernel then rescales the passes against each other.
+                size_t pitch, int n, int K, int NSG, double* __restrict__ ll_out, int mode, const float* den_in,
+                float* den_out) {
+    // K / NSG / b_img / ck / memb describe ONE pass of at most 64 clusters.  More than 64 clusters take 2P - 1 launches
+    // for P passes, and every responsibility is written exactly once (round 1 normalised each pass within itself and
+    // rescaled all of them in a read-modify-write pass over the memberships):
+    //   mode 1 (passes 0 .. P-2)  log-denominator only: den_out[e] = ln(sum_k exp(logit)) (+ den_in[e] in log space), no stores
+    //   mode 2 (pass P-1)         its own log-sum-exp joined with den_in[e] (all other passes): final responsibilities of this
+    //                             pass, den_out[e] = the event's total log-denominator, log-likelihood
+    //   mode 3 (passes 0 .. P-2)  responsibilities against the known total den_in[e]: no log-sum-exp, no exchange
+    //   mode 0                    single pass (K <= 64)
     using C = ECfg<D>;
     constexpr int NWG = C::NWG;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -765,24 +771,42 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                     mx = fmaxf(mx, l);
                 }
             }
-            // log-sum-exp over the clusters (estep2, gaussian_kernel.cu:481-503): local part, then the two warpgroups combine
-            float sm = 0.f;
+            float scale;
+            if (mode == 3) {
+                // the event's total log-denominator is known: gamma = 2^(l2 - denom * log2 e)
+                const float d2 = e < n ? den_in[e] * 1.4426950408889634f : 0.f;
 #pragma unroll
-            for (int j = 0; j < C::LPT; j++) { lg[j] = ex2_approx(lg[j] - mx); sm += lg[j]; }
-            float2* exb = ex + (it & 1) * (NWG * 128);
-            exb[wg * 128 + row] = make_float2(mx, sm);
-            named_bar_sync(1, NWG * 128);
-            const float2 o = exb[(wg ^ 1) * 128 + row];
-            const float M = fmaxf(mx, o.x);
-            const float own = ex2_approx(mx - M);
-            const float S = sm * own + o.y * ex2_approx(o.x - M);
-            const float denom = fmaf(M, kLn2, logf(S));              // :490-494, back in natural units
-            const float scale = own / S;                             // exp(l - denom) = 2^(l2 - mx) * 2^(mx - M) / S
-            if (e < n) {
-                if (wg == 0) {
-                    if (den_out) den_out[e] = denom;
-                    else ll_acc += (double)denom;
+                for (int j = 0; j < C::LPT; j++) lg[j] = ex2_approx(lg[j] - d2);
+                scale = 1.0f;
+            } else {
+                // log-sum-exp over the clusters (estep2, gaussian_kernel.cu:481-503): local part, then the two warpgroups combine
+                float sm = 0.f;
+#pragma unroll
+                for (int j = 0; j < C::LPT; j++) { lg[j] = ex2_approx(lg[j] - mx); sm += lg[j]; }
+                float2* exb = ex + (it & 1) * (NWG * 128);
+                exb[wg * 128 + row] = make_float2(mx, sm);
+                // den_in may alias den_out (running log-denominator updated in place by warpgroup 0): both warpgroups read
+                // it BEFORE the barrier, the write comes after
+                const float dx = (mode != 0 && den_in != nullptr && e < n) ? den_in[e] : 0.f;
+                named_bar_sync(1, NWG * 128);
+                const float2 o = exb[(wg ^ 1) * 128 + row];
+                const float M = fmaxf(mx, o.x);
+                const float own = ex2_approx(mx - M);
+                const float S = sm * own + o.y * ex2_approx(o.x - M);
+                float denom = fmaf(M, kLn2, logf(S));                // :490-494, back in natural units
+                scale = own / S;                                     // exp(l - denom) = 2^(l2 - mx) * 2^(mx - M) / S
+                if (mode != 0 && e < n) {
+                    if (den_in != nullptr) {                         // join with the other passes' log-denominator
+                        const float g = fmaxf(denom, dx);
+                        const float tot = g + logf(__expf(denom - g) + __expf(dx - g));
+                        scale *= __expf(denom - tot);
+                        denom = tot;
+                    }
+                    if (wg == 0) den_out[e] = denom;
                 }
+                if (wg == 0 && e < n && (mode == 0 || mode == 2)) ll_acc += (double)denom;
+            }
+            if (e < n && mode != 1) {
                 // Rows [K, 8*ceil(K/8)) are written too (zeros of the padding clusters): the buffer is allocated in
                 // multiples of 8 rows, which keeps the 8 stores of a group unpredicated.
                 float* gp = memb + (size_t)(wg * C::CW) * pitch + e;      // row of this warpgroup's first cluster
@@ -799,7 +823,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                 }
             }
         }
-        if (wg == 0 && den_out == nullptr) {
+        if (wg == 0 && (mode == 0 || mode == 2)) {
             ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 16);
             ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 8);
             ll_acc = ll_acc + __shfl_down_sync(0xffffffffu, ll_acc, 4);
@@ -811,48 +835,6 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc<512>(tmem);
-}
-
-// More than 64 clusters: joins the per-pass normalisations.  den[p][e] = ln sum_{k in pass p} exp(logit);
-// the event's denominator is the log-sum-exp over the passes (estep2, gaussian_kernel.cu:481-503) and every
-// responsibility of pass p is multiplied by exp(den_p - denom).
-constexpr int kEMaxPass = GMM_MAX_CLUSTERS / 64;
-__global__ void __launch_bounds__(256)
-estep_tc_combine_kernel(float* __restrict__ memb, size_t pitch, int n, int K, int NP, const float* __restrict__ den,
-                        double* __restrict__ ll_out) {
-    __shared__ double red[8];
-    double ll = 0.0;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-        float dp[kEMaxPass];
-        float M = -INFINITY;
-#pragma unroll
-        for (int p = 0; p < kEMaxPass; p++) {
-            dp[p] = p < NP ? den[(size_t)p * pitch + e] : -INFINITY;
-            M = fmaxf(M, dp[p]);
-        }
-        float S = 0.f;
-#pragma unroll
-        for (int p = 0; p < kEMaxPass; p++) S += __expf(dp[p] - M);
-        const float denom = M + logf(S);
-        ll += (double)denom;
-#pragma unroll
-        for (int p = 0; p < kEMaxPass; p++) {
-            if (p < NP) {
-                const float f = __expf(dp[p] - denom);
-                const int kend = min(K, (p + 1) * 64);
-                float* g = memb + (size_t)(p * 64) * pitch + e;
-                for (int k = p * 64; k < kend; k++, g += pitch) *g *= f;
-            }
-        }
-    }
-    for (int o = 16; o > 0; o >>= 1) ll += __shfl_down_sync(0xffffffffu, ll, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ll;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int w = 0; w < 8; w++) t += red[w];
-        atomicAdd(ll_out, t);
-    }
 }
 
 // ---------------------------------------------------------------------------
@@ -889,7 +871,7 @@ struct TcState {
     bool h2d_pending = false;
     float* d_ck = nullptr;           // [passes][ck 64 | mult 64]: additive constant and quadratic-form multiplier per cluster
     float* h_ck = nullptr;           // pinned mirror
-    float* d_den = nullptr;          // [passes][memb_pitch] per-pass log-denominators (Kmax > 64 only)
+    float* d_den = nullptr;          // [memb_pitch] running / total log-denominator per event (Kmax > 64 only)
     int e_ck_len = 0;                // Kmax rounded up to whole passes of 64
     int e_NG = 0;
     int host_threads = 8;
@@ -967,7 +949,7 @@ int tc_create(TcState** out, const float* d_x_aos, const float* d_x_soa, int n, 
         t->d_bimg = t->d_opnd + ck_bytes;
         t->h_bimg = t->h_opnd + ck_bytes;
         TC_CUDA_TRY(cudaEventCreateWithFlags(&t->ev_h2d, cudaEventDisableTiming));
-        if (passes > 1) TC_CUDA_TRY(cudaMalloc(&t->d_den, sizeof(float) * (size_t)passes * memb_pitch));
+        if (passes > 1) TC_CUDA_TRY(cudaMalloc(&t->d_den, sizeof(float) * memb_pitch));
         t->emap_ok = true;
     }
     const int rpp = 1 + 2 * (D / 4) + (D / 4) * (D / 2), nrows = 4 * ((rpp + 7) / 8) * 8;
@@ -1250,17 +1232,21 @@ static int launch_estep_d(TcState* t, int K, double* d_ll, cudaStream_t stream) 
     if (grid < 1) grid = 1;
     const int NP = (K + 63) / 64;
     if (NP > 1 && !t->d_den) return fail(GMM_ERR_STATE, "tensor E-step: context was created for at most 64 clusters");
-    for (int p = 0; p < NP; p++) {
+    // P passes of 64 clusters: log-denominators of passes 0 .. P-2 (mode 1), then the last pass writes its final
+    // responsibilities and the events' total log-denominators (mode 2, or mode 0 when P = 1), then passes 0 .. P-2 write
+    // theirs against those totals (mode 3): 2P - 1 launches, every responsibility stored once
+    auto launch = [&](int p, int mode, const float* den_in, float* den_out) {
         const int Kp = K - 64 * p < 64 ? K - 64 * p : 64;
         estep_tc_kernel<D><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(
             t->d_x, t->d_bimg + (size_t)p * C::MAXSG * C::B_SG, t->d_ck + 128 * p, t->d_shift_f, t->d_inv_scale_f,
-            t->d_memb + (size_t)(64 * p) * t->memb_pitch, t->memb_pitch, t->n, Kp, (Kp + C::GB - 1) / C::GB, d_ll,
-            NP > 1 ? t->d_den + (size_t)p * t->memb_pitch : nullptr);
-        TC_CUDA_TRY(cudaGetLastError());
-    }
-    if (NP > 1) {
-        estep_tc_combine_kernel<<<t->num_sms * 8, 256, 0, stream>>>(t->d_memb, t->memb_pitch, t->n, K, NP, t->d_den, d_ll);
-        TC_CUDA_TRY(cudaGetLastError());
+            t->d_memb + (size_t)(64 * p) * t->memb_pitch, t->memb_pitch, t->n, Kp, (Kp + C::GB - 1) / C::GB, d_ll, mode, den_in, den_out);
+        return cudaGetLastError();
+    };
+    if (NP == 1) TC_CUDA_TRY(launch(0, 0, nullptr, nullptr));
+    else {
+        for (int p = 0; p + 1 < NP; p++) TC_CUDA_TRY(launch(p, 1, p ? t->d_den : nullptr, t->d_den));
+        TC_CUDA_TRY(launch(NP - 1, 2, t->d_den, t->d_den));
+        for (int p = 0; p + 1 < NP; p++) TC_CUDA_TRY(launch(p, 3, t->d_den, nullptr));
     }
     return GMM_OK;
 }

@@ -508,3 +508,31 @@ def test_cli_two_gpus_equals_one(loaded, tmp_path):
         assert abs(a["pi"] - b["pi"]) <= 2e-6
         np.testing.assert_allclose(a["means"], b["means"], atol=1.1e-3)
         np.testing.assert_allclose(np.array(a["R"]), np.array(b["R"]), atol=1.1e-3)
+
+
+@pytest.mark.parametrize("N,D,K", [(70_001, 24, 64), (33_333, 8, 5)])
+def test_tensor_steps_rerun_bit_stable(loaded, N, D, K):
+    """Stress of the asynchronous hand-overs inside the tensor kernels (TMA stage release, operand stages, accumulator
+    drains, the E-step's TMEM hand-over): 40 E-step + M-step repetitions from identical inputs must be bit-identical —
+    a refill that overtakes a pending load, or a drain that races an MMA, shows up as run-to-run differences (the
+    stage-release race of round 1 did)."""
+    pkg = loaded
+    ev = pkg.synth.make_blobs(N, D, min(K, 8), seed=321)
+    with pkg.Engine(ev, K) as eng:
+        eng.set_option("path", pkg.PATH_TENSOR)
+        start = eng.seed(K)
+        first = None
+        for rep in range(40):
+            eng.set_clusters(K, start)
+            ll = eng.estep(K)
+            eng.mstep(K)
+            got = eng.get_clusters(K, with_memberships=(rep % 10 == 0))
+            cur = (ll, got.N.copy(), got.means.copy(), got.R.copy())
+            if first is None:
+                first, memb0 = cur, got.memberships.copy()
+            else:
+                assert cur[0] == first[0], rep
+                for a, b in zip(cur[1:], first[1:]):
+                    np.testing.assert_array_equal(a, b, err_msg=f"repetition {rep}")
+                if got.memberships is not None:
+                    np.testing.assert_array_equal(got.memberships, memb0, err_msg=f"repetition {rep}")
