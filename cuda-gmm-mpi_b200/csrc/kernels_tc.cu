@@ -541,6 +541,12 @@ template <int D> struct ECfg {
     static_assert(QCOL + 2 * 64 <= 512, "TMEM columns");
 };
 
+// GMM_ESTEP_EXP (build-time, timing experiments only — results are wrong): 1 = no responsibility stores, 2 = the
+// log-sum-exp stage only drains q, 3 = the squares stage skips the fma.f32x2 work.  Isolates the cost of each stage.
+#ifndef GMM_ESTEP_EXP
+#define GMM_ESTEP_EXP 0
+#endif
+
 template <int D>
 __global__ void __launch_bounds__(768, 1)
 estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_img, const float* __restrict__ ck,
@@ -593,7 +599,6 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
         for (int g = 0; g < NSG * C::CP; g++) tma_load_1d(smem + C::OFF_B + g * C::B_BLOCK, b_img + (size_t)g * C::B_BLOCK, C::B_BLOCK, b_full);
     }
     if (warp == 2) tmem_alloc<512>(tmem_slot);
-    mbar_wait(b_full, 0);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -607,6 +612,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(128, C::N, false, false);
             uint32_t pe = (1u << C::NBUF) - 1u;                // wait parity of acc_empty[b], one bit per buffer
+            mbar_wait(b_full, 0);                              // the resident B image has landed (the converters did not wait for it)
             for (int it = 0; it < my_tiles; it++) {
                 const int as = it & 1, aph = (it >> 1) & 1;
                 mbar_wait_parked(&a_full[as], aph, 200);
@@ -723,7 +729,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                         if (lane == 0) mbar_arrive(&acc_empty[buf]);   // the block is in registers: hand the buffer back
                         buf = buf + 1 == C::NBUF ? 0 : buf + 1;
 #pragma unroll
-                        for (int i = 0; i < C::CW; i++) {
+                        for (int i = 0; i < (GMM_ESTEP_EXP == 3 ? 1 : C::CW); i++) {
                             sq_acc2(qa[i], v[i * 8 + 0], v[i * 8 + 1]);
                             sq_acc2(qb[i], v[i * 8 + 2], v[i * 8 + 3]);
                             sq_acc2(qa[i], v[i * 8 + 4], v[i * 8 + 5]);
@@ -760,6 +766,10 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&q_empty[tb]);
+#if GMM_ESTEP_EXP == 2
+            if (lg[0] == 12345.678f) memb[e] = lg[1];
+            continue;
+#endif
             float mx = -INFINITY;
 #pragma unroll
             for (int sg = 0; sg < C::MAXSG; sg++) {
@@ -806,7 +816,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                 }
                 if (wg == 0 && e < n && (mode == 0 || mode == 2)) ll_acc += (double)denom;
             }
-            if (e < n && mode != 1) {
+            if (e < n && mode != 1 && (GMM_ESTEP_EXP != 1 || scale == 12345.678f)) {
                 // Rows [K, 8*ceil(K/8)) are written too (zeros of the padding clusters): the buffer is allocated in
                 // multiples of 8 rows, which keeps the 8 stores of a group unpredicated.
                 float* gp = memb + (size_t)(wg * C::CW) * pitch + e;      // row of this warpgroup's first cluster
