@@ -13,7 +13,11 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -92,6 +96,96 @@ struct EventPool {
     void destroy() { for (cudaEvent_t e : free_list) cudaEventDestroy(e); free_list.clear(); }
 };
 
+// Persistent worker team for the per-iteration host finalisation (K independent clusters, a few microseconds each).
+// The workers SPIN on a generation counter for a few milliseconds after each job — an EM iteration hands them the
+// next one within that window — and only then block on a condition variable.  An OpenMP parallel region costs a
+// futex wake-up per thread and iteration when the runtime's wait policy is passive (torchrun exports OMP_NUM_THREADS=1
+// and the measured finalisation went from 0.05 ms to 0.33 ms per iteration at 2 ranks).
+class HostPool {
+public:
+    explicit HostPool(int nthreads) { resize(nthreads); }
+    ~HostPool() { stop(); }
+    int size() const { return (int)workers_.size() + 1; }
+    void resize(int nthreads) {
+        if (nthreads < 1) nthreads = 1;
+        if (nthreads == size() && started_) return;
+        stop();
+        quit_.store(false);
+        started_ = true;
+        for (int i = 1; i < nthreads; i++) workers_.emplace_back([this] { worker(); });
+    }
+    // fn(i) for i in [0, n), spread dynamically over the team (the caller takes part); returns when all are done
+    void run(int n, const std::function<void(int)>& fn) {
+        if (n <= 0) return;
+        if (workers_.empty() || n == 1) { for (int i = 0; i < n; i++) fn(i); return; }
+        // a worker may still be on its way out of the previous job's loop: everything it could read is published
+        // before `next_` restarts (release), and the completion count is reset before any new item can be taken
+        fn_ = &fn; n_ = n;
+        done_.store(0, std::memory_order_relaxed);
+        next_.store(0, std::memory_order_release);
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            gen_.fetch_add(1, std::memory_order_release);
+        }
+        cv_.notify_all();
+        work();
+        while (done_.load(std::memory_order_acquire) < n_) cpu_relax();
+    }
+private:
+    static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    void work() {
+        for (;;) {
+            const int i = next_.fetch_add(1, std::memory_order_acq_rel);
+            if (i >= n_) break;
+            (*fn_)(i);
+            done_.fetch_add(1, std::memory_order_release);
+        }
+    }
+    void worker() {
+        unsigned long long seen = gen_.load(std::memory_order_acquire);
+        for (;;) {
+            // spin for up to ~4 ms, then sleep
+            const auto t0 = std::chrono::steady_clock::now();
+            unsigned long long g;
+            int spins = 0;
+            while ((g = gen_.load(std::memory_order_acquire)) == seen && !quit_.load(std::memory_order_relaxed)) {
+                cpu_relax();
+                if ((++spins & 1023) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(4)) {
+                    std::unique_lock<std::mutex> lk(m_);
+                    cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen || quit_.load(); });
+                }
+            }
+            if (quit_.load()) return;
+            seen = g;
+            work();
+        }
+    }
+    void stop() {
+        if (!started_) return;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            quit_.store(true);
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+        workers_.clear();
+        started_ = false;
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::atomic<unsigned long long> gen_{0};
+    std::atomic<int> next_{0}, done_{0};
+    std::atomic<bool> quit_{false};
+    const std::function<void(int)>* fn_ = nullptr;
+    int n_ = 0;
+    bool started_ = false;
+};
+
 }  // namespace gmm
 
 using namespace gmm;
@@ -143,6 +237,7 @@ struct gmm_ctx {
     long long mstep_tensor = 0, mstep_simt = 0;                   // M-step launches by kernel
     long long iterations = 0;
     TcState* tc = nullptr;       // tensor-core path state (kernels_tc.cuh)
+    HostPool* pool = nullptr;    // worker team of the per-iteration host finalisation (created on first use)
     bool estep_tensor_ready = false;   // the tensor E-step operand of the current parameters is uploaded
 };
 
@@ -236,16 +331,25 @@ static int upload_params(gmm_ctx* c, int K, bool with_constants = false, bool wi
             if (with_finalize)                     // pi needs every N[k] = (float)S0 before the per-cluster loop
                 for (int k = 0; k < K; k++) c->host.N[k] = (float)c->h_stats[(size_t)k * c->F];
             if (with_constants) mixing_weights(K, &c->host);
-            const int kp = tc_params_padded(c->tc, K), nt = c->host_threads, D = c->D;
-            int bad = 0;
-            (void)nt;
-#pragma omp parallel for schedule(static) num_threads(nt) reduction(max : bad) if (nt > 1 && K >= 8)
-            for (int k = 0; k < kp; k++) {
+            const int kp = tc_params_padded(c->tc, K), D = c->D;
+            std::atomic<int> bad_all{0};
+            const int nt = K >= 8 ? c->host_threads : 1;
+            if (!c->pool) c->pool = new HostPool(nt);
+            else c->pool->resize(nt);
+            c->pool->run(kp, [&](int k) {
                 if (with_finalize && k < K) finalize_cluster(c->h_stats, c->shift, k, D, &c->host);
-                if (with_constants && k < K) constants_cluster(k, D, &c->host);
-                const int b = tc_params_cluster(c->tc, &c->host, k, K);
-                bad = b > bad ? b : bad;
-            }
+                int b;
+                double W[GMM_MAX_DIMENSIONS * GMM_MAX_DIMENSIONS];
+                if (with_constants && k < K && constants_cluster_spd(k, D, &c->host, W)) {
+                    b = tc_params_cluster_w(c->tc, &c->host, k, K, W);      // one factorisation serves Rinv, ln det and the operand
+                } else {
+                    if (with_constants && k < K) constants_cluster(k, D, &c->host);
+                    b = tc_params_cluster(c->tc, &c->host, k, K);
+                }
+                int cur = bad_all.load(std::memory_order_relaxed);
+                while (b > cur && !bad_all.compare_exchange_weak(cur, b)) {}
+            });
+            const int bad = bad_all.load();
             with_constants = with_finalize = false;
             rc = tc_params_commit(c->tc, K, bad, c->stream);
         }
@@ -597,6 +701,7 @@ void gmm_destroy(gmm_ctx* c) {
     collect_all(c);
     if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
     tc_destroy(c->tc);
+    delete c->pool;
     cudaFree(c->d_x_aos); cudaFree(c->d_x_soa); cudaFree(c->d_memb); cudaFree(c->d_memb_saved);
     cudaFree(c->d_epack); cudaFree(c->d_stats); cudaFree(c->d_shift);
     if (c->h_epack) cudaFreeHost(c->h_epack);

@@ -77,6 +77,50 @@ void constants_cluster(int k, int D, clusters_t* c) {
     c->constant[k] = (float)(-D * 0.5 * std::log(2.0 * kPi) - 0.5 * ld);   // :241
 }
 
+// The same for a symmetric positive definite R through ONE factorisation: R = U U^T (U upper triangular, "reverse"
+// Cholesky), W = U^-1 (upper triangular), Rinv = W^T W, ln det R = 2 sum ln U_ii — a third of the arithmetic of the
+// LU inverse plus the separate factorisation of Rinv the tensor E-step's operand needs (W is handed to it directly).
+// Returns false (nothing written) when R is not positive definite: the caller then takes the no-pivot LU path, whose
+// semantics on such matrices are the reference's (invert_matrix.cpp:25-101).
+bool constants_cluster_spd(int k, int D, clusters_t* c, double* W /* [D][D] out */) {
+    double U[GMM_MAX_DIMENSIONS][GMM_MAX_DIMENSIONS];
+    const float* R = c->R + (size_t)k * D * D;
+    double ld = 0.0;
+    for (int j = D - 1; j >= 0; j--) {
+        double d = R[j * D + j];
+        for (int m = j + 1; m < D; m++) d -= U[j][m] * U[j][m];
+        if (!(d > 0.0) || !std::isfinite(d)) return false;
+        const double piv = std::sqrt(d), rp = 1.0 / piv;
+        U[j][j] = piv;
+        ld += std::log(piv);
+        for (int i = 0; i < j; i++) {
+            double v = 0.5 * ((double)R[i * D + j] + (double)R[j * D + i]);
+            for (int m = j + 1; m < D; m++) v -= U[i][m] * U[j][m];
+            U[i][j] = v * rp;
+        }
+    }
+    // W = U^-1 (upper triangular), column by column: W[i][j] = -(sum_{m=i+1..j} U[i][m] W[m][j]) / U[i][i]
+    for (int j = 0; j < D; j++) {
+        for (int i = D - 1; i > j; i--) W[i * D + j] = 0.0;
+        W[j * D + j] = 1.0 / U[j][j];
+        for (int i = j - 1; i >= 0; i--) {
+            double v = 0.0;
+            for (int m = i + 1; m <= j; m++) v -= U[i][m] * W[m * D + j];
+            W[i * D + j] = v / U[i][i];
+        }
+    }
+    float* Ri = c->Rinv + (size_t)k * D * D;
+    for (int i = 0; i < D; i++)
+        for (int j = i; j < D; j++) {                   // (W^T W)[i][j] = sum_{m <= i} W[m][i] W[m][j]
+            double v = 0.0;
+            for (int m = 0; m <= i; m++) v += W[m * D + i] * W[m * D + j];
+            Ri[i * D + j] = (float)v;
+            Ri[j * D + i] = (float)v;
+        }
+    c->constant[k] = (float)(-D * 0.5 * std::log(2.0 * kPi) - 0.5 * (2.0 * ld));   // gaussian_kernel.cu:241
+    return true;
+}
+
 void mixing_weights(int K, clusters_t* c) {
     double sum = 0;                                                            // :176-181
     for (int k = 0; k < K; k++) sum += c->N[k];
@@ -87,7 +131,10 @@ void mixing_weights(int K, clusters_t* c) {
 void constants_from_R(int K, int D, clusters_t* c, int num_threads) {
     (void)num_threads;
 #pragma omp parallel for schedule(static) num_threads(num_threads) if (K >= 8 && num_threads > 1)
-    for (int k = 0; k < K; k++) constants_cluster(k, D, c);
+    for (int k = 0; k < K; k++) {
+        double W[GMM_MAX_DIMENSIONS * GMM_MAX_DIMENSIONS];
+        if (!constants_cluster_spd(k, D, c, W)) constants_cluster(k, D, c);     // not positive definite: the no-pivot LU semantics
+    }
     mixing_weights(K, c);
 }
 

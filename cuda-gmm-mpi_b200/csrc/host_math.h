@@ -31,6 +31,9 @@ void constants_from_R(int K, int D, clusters_t* c, int num_threads);
 // The two parts of constants_from_R, for callers that run their own loop over the clusters:
 // inverse + constant of one cluster, and the mixing weights pi (needs every N[k]).
 void constants_cluster(int k, int D, clusters_t* c);
+// Same results for a symmetric positive definite R from one (reverse) Cholesky factorisation; also returns the
+// upper-triangular W with Rinv = W^T W.  false = not positive definite, nothing written (use constants_cluster).
+bool constants_cluster_spd(int k, int D, clusters_t* c, double* W);
 // N, mean and covariance of ONE cluster from the packed statistics (the loop body of finalize_from_stats).
 void finalize_cluster(const double* stats, const double* shift, int k, int D, clusters_t* c);
 void mixing_weights(int K, clusters_t* c);

@@ -1084,8 +1084,10 @@ static inline float h2f_bits(uint16_t h) {
 
 // Operand rows of cluster k (k >= K: padding cluster of the last supergroup).  Returns 0, 1 (Rinv not positive
 // definite) or 2 (factor outside the FP16 range).  Clusters are independent: callers may run this in parallel.
+// Wext (optional): the upper-triangular factor W with Rinv = W^T W already computed by the caller in double (row-major
+// [D][D]); otherwise it is derived here from host->Rinv.
 template <int D>
-static int bimg_cluster(TcState* t, const clusters_t* host, int k, int K) {
+static int bimg_cluster(TcState* t, const clusters_t* host, int k, int K, const double* Wext = nullptr) {
     using C = ECfg<D>;
     int bad = 0;
     {
@@ -1103,10 +1105,15 @@ static int bimg_cluster(TcState* t, const clusters_t* host, int k, int K) {
         }
         double A[D][D], Gc[D][D];
         const float* Ri = host->Rinv + (size_t)k * D * D;
-        for (int r = 0; r < D; r++)
-            for (int j = 0; j < D; j++) { A[r][j] = 0.5 * ((double)Ri[r * D + j] + (double)Ri[j * D + r]); Gc[r][j] = 0.0; }
         bool ok = true;
-        for (int j = 0; j < D; j++) {                    // right-looking Cholesky A = Gc Gc^T (axpy updates vectorise)
+        if (Wext) {                                      // W = Gc^T
+            for (int r = 0; r < D; r++)
+                for (int j = 0; j < D; j++) Gc[r][j] = Wext[j * D + r];
+        } else {
+            for (int r = 0; r < D; r++)
+                for (int j = 0; j < D; j++) { A[r][j] = 0.5 * ((double)Ri[r * D + j] + (double)Ri[j * D + r]); Gc[r][j] = 0.0; }
+        }
+        for (int j = 0; j < D && !Wext; j++) {                    // right-looking Cholesky A = Gc Gc^T (axpy updates vectorise)
             const double d = A[j][j];
             if (!(d > 0.0) || !std::isfinite(d)) { ok = false; break; }
             const double piv = std::sqrt(d), rp = 1.0 / piv;
@@ -1174,11 +1181,11 @@ static int bimg_cluster(TcState* t, const clusters_t* host, int k, int K) {
     return bad;
 }
 
-static int bimg_cluster_any(TcState* t, const clusters_t* host, int k, int K) {
+static int bimg_cluster_any(TcState* t, const clusters_t* host, int k, int K, const double* Wext = nullptr) {
     switch (t->D) {
-        case 8: return bimg_cluster<8>(t, host, k, K);
-        case 16: return bimg_cluster<16>(t, host, k, K);
-        case 24: return bimg_cluster<24>(t, host, k, K);
+        case 8: return bimg_cluster<8>(t, host, k, K, Wext);
+        case 16: return bimg_cluster<16>(t, host, k, K, Wext);
+        case 24: return bimg_cluster<24>(t, host, k, K, Wext);
         default: return 3;
     }
 }
@@ -1200,6 +1207,7 @@ int tc_params_begin(TcState* t, int K, cudaStream_t stream) {
 }
 int tc_params_padded(const TcState*, int K) { return (K + 15) / 16 * 16; }
 int tc_params_cluster(TcState* t, const clusters_t* host, int k, int K) { return bimg_cluster_any(t, host, k, K); }
+int tc_params_cluster_w(TcState* t, const clusters_t* host, int k, int K, const double* W) { return bimg_cluster_any(t, host, k, K, W); }
 int tc_params_commit(TcState* t, int K, int bad, cudaStream_t stream) {
     if (bad == 1) return fail(GMM_ERR_STATE, "tensor E-step: inverse covariance of a cluster is not positive definite");
     if (bad == 2) return fail(GMM_ERR_STATE, "tensor E-step: whitening factor exceeds the FP16 range");

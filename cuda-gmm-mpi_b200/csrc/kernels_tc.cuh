@@ -33,6 +33,9 @@ int  tc_upload_params(TcState*, const clusters_t* host, int K, cudaStream_t stre
 int  tc_params_begin(TcState*, int K, cudaStream_t stream);
 int  tc_params_padded(const TcState*, int K);
 int  tc_params_cluster(TcState*, const clusters_t* host, int k, int K);
+// The same with the upper-triangular factor W (Rinv = W^T W, double, row-major [D][D]) supplied by the caller
+// (constants_cluster_spd): no second factorisation of the inverse.
+int  tc_params_cluster_w(TcState*, const clusters_t* host, int k, int K, const double* W);
 int  tc_params_commit(TcState*, int K, int bad, cudaStream_t stream);
 int  tc_launch_estep(TcState*, int K, double* d_ll, cudaStream_t stream);
 // Accumulates sum_n g[k][n] * phi_f(x_n - shift) into d_stats[k*F + f] (double, original units).
