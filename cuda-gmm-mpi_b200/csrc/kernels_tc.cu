@@ -533,7 +533,7 @@ template <int D> struct ECfg {
     static constexpr int B_SG = CP * B_BLOCK;
     static constexpr int OFF_B = 0;
     static constexpr int OFF_A = OFF_B + MAXSG * B_SG;
-    static constexpr int OFF_CK = OFF_A + 2 * A_STAGE;        // float2[64]: (constant + ln(pi)) * log2(e), -0.5 * log2(e) / scale_k^2
+    static constexpr int OFF_CK = OFF_A + 2 * A_STAGE;        // float[64] (constant + ln(pi)) * log2(e), then float[64] -0.5 * log2(e) / scale_k^2
     static constexpr int OFF_EX = OFF_CK + 512;               // exchange: [2 parity][NWG][128] x (max, sum)
     static constexpr int OFF_BAR = OFF_EX + 2 * NWG * 128 * 8;
     static constexpr int SMEM_BYTES = OFF_BAR + 512;
@@ -573,7 +573,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
     uint64_t* q_full = bars + 11;       // [2]  8 square warps: q of a tile is in TMEM
     uint64_t* q_empty = bars + 13;      // [2]  8 log-sum-exp warps: q of a tile is in their registers
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
-    float2* ck_s = reinterpret_cast<float2*>(smem + C::OFF_CK);
+    float* ck_s = reinterpret_cast<float*>(smem + C::OFF_CK);          // [64] additive logit constants, [64] multipliers
     float2* ex = reinterpret_cast<float2*>(smem + C::OFF_EX);
     float* sh_s = reinterpret_cast<float*>(smem + C::OFF_BAR + 128);   // [32] shift, [32] inverse scale
     float* isc_s = sh_s + 32;
@@ -591,7 +591,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
     }
     // base-2 logits in the epilogue: l2 = ck * log2(e) + (-0.5 * log2(e) / scale_k^2) * |scale_k * y|^2   (the per-cluster
     // power-of-two scale_k keeps the FP16 whitening factors in range whatever the cluster's width, see bimg_cluster)
-    if (threadIdx.x < 64) ck_s[threadIdx.x] = make_float2(ck[threadIdx.x] * 1.4426950408889634f, ck[64 + threadIdx.x]);
+    if (threadIdx.x < 64) { ck_s[threadIdx.x] = ck[threadIdx.x] * 1.4426950408889634f; ck_s[64 + threadIdx.x] = ck[64 + threadIdx.x]; }
     if (threadIdx.x < D) { sh_s[threadIdx.x] = shift_f[threadIdx.x]; isc_s[threadIdx.x] = inv_scale_f[threadIdx.x]; }
     __syncthreads();
     if (threadIdx.x == 0) {                    // resident B operand: one TMA bulk copy per block
@@ -758,41 +758,61 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
         for (int it = 0; it < my_tiles; it++) {
             const int tb = it & 1;
             const long long e = (long long)((int)blockIdx.x + it * (int)gridDim.x) * 128 + row;
-            float lg[C::LPT];                                  // q, then logits in base 2 (ck_s is pre-multiplied by log2 e)
+            // q, then base-2 logits, then 2^(logit - max), as PACKED pairs of neighbouring clusters (fma / add / mul .f32x2:
+            // half the instructions and FMA-pipe cycles of this stage; the pipe is shared with the squares)
+            uint64_t lgp[C::LPT / 2];
             mbar_wait_parked(&q_full[tb], (it >> 1) & 1, 200);
             tc_fence_after();
-            tmem_ld_32x32(tmem + lane_base + C::QCOL + tb * 64 + wg * C::LPT, *reinterpret_cast<uint32_t(*)[32]>(&lg[0]));
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&q_empty[tb]);
-#if GMM_ESTEP_EXP == 2
-            if (lg[0] == 12345.678f) memb[e] = lg[1];
-            continue;
-#endif
-            float mx = -INFINITY;
+            {
+                uint32_t qraw[C::LPT];
+                tmem_ld_32x32(tmem + lane_base + C::QCOL + tb * 64 + wg * C::LPT, qraw);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&q_empty[tb]);
 #pragma unroll
-            for (int sg = 0; sg < C::MAXSG; sg++) {
+                for (int sg = 0; sg < C::MAXSG; sg++) {
+                    if (sg < NSG) {
+                        const float4* cp = reinterpret_cast<const float4*>(ck_s + sg * C::GB + wg * C::CW);
+                        const float4* mp = reinterpret_cast<const float4*>(ck_s + 64 + sg * C::GB + wg * C::CW);
+                        const float4 c0 = cp[0], c1 = cp[1], m0 = mp[0], m1 = mp[1];
+                        const int j = sg * C::CW;
+                        lgp[j / 2 + 0] = ffma2(pack2f(m0.x, m0.y), pack2u(qraw[j + 0], qraw[j + 1]), pack2f(c0.x, c0.y));
+                        lgp[j / 2 + 1] = ffma2(pack2f(m0.z, m0.w), pack2u(qraw[j + 2], qraw[j + 3]), pack2f(c0.z, c0.w));
+                        lgp[j / 2 + 2] = ffma2(pack2f(m1.x, m1.y), pack2u(qraw[j + 4], qraw[j + 5]), pack2f(c1.x, c1.y));
+                        lgp[j / 2 + 3] = ffma2(pack2f(m1.z, m1.w), pack2u(qraw[j + 6], qraw[j + 7]), pack2f(c1.z, c1.w));
+                    } else {                                   // columns of unused supergroups are not written
 #pragma unroll
-                for (int i = 0; i < C::CW; i++) {
-                    const float2 cm = ck_s[sg * C::GB + wg * C::CW + i];
-                    const float l = sg < NSG ? fmaf(cm.y, lg[sg * C::CW + i], cm.x) : -INFINITY;   // columns of unused supergroups are not written
-                    lg[sg * C::CW + i] = l;
-                    mx = fmaxf(mx, l);
+                        for (int u = 0; u < C::CW / 2; u++) lgp[sg * C::CW / 2 + u] = pack2f(-INFINITY, -INFINITY);
+                    }
                 }
             }
+            float mx = -INFINITY;
+#pragma unroll
+            for (int u = 0; u < C::LPT / 2; u++) { mx = fmaxf(mx, lo2f(lgp[u])); mx = fmaxf(mx, hi2f(lgp[u])); }
             float scale;
             if (mode == 3) {
                 // the event's total log-denominator is known: gamma = 2^(l2 - denom * log2 e)
                 const float d2 = e < n ? den_in[e] * 1.4426950408889634f : 0.f;
+                const uint64_t nd = pack2f(-d2, -d2);
 #pragma unroll
-                for (int j = 0; j < C::LPT; j++) lg[j] = ex2_approx(lg[j] - d2);
+                for (int u = 0; u < C::LPT / 2; u++) {
+                    const uint64_t t2 = fadd2(lgp[u], nd);
+                    lgp[u] = pack2f(ex2_approx(lo2f(t2)), ex2_approx(hi2f(t2)));
+                }
                 scale = 1.0f;
             } else {
                 // log-sum-exp over the clusters (estep2, gaussian_kernel.cu:481-503): local part, then the two warpgroups combine
-                float sm = 0.f;
+                const uint64_t nm = pack2f(-mx, -mx);
+                uint64_t s0 = 0ull, s1 = 0ull;                       // two packed running sums (four independent chains)
 #pragma unroll
-                for (int j = 0; j < C::LPT; j++) { lg[j] = ex2_approx(lg[j] - mx); sm += lg[j]; }
+                for (int u = 0; u < C::LPT / 2; u++) {
+                    const uint64_t t2 = fadd2(lgp[u], nm);
+                    lgp[u] = pack2f(ex2_approx(lo2f(t2)), ex2_approx(hi2f(t2)));
+                    if (u & 1) s1 = fadd2(s1, lgp[u]); else s0 = fadd2(s0, lgp[u]);
+                }
+                const uint64_t s2 = fadd2(s0, s1);
+                const float sm = lo2f(s2) + hi2f(s2);
                 float2* exb = ex + (it & 1) * (NWG * 128);
                 exb[wg * 128 + row] = make_float2(mx, sm);
                 // den_in may alias den_out (running log-denominator updated in place by warpgroup 0): both warpgroups read
@@ -820,14 +840,17 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                 // Rows [K, 8*ceil(K/8)) are written too (zeros of the padding clusters): the buffer is allocated in
                 // multiples of 8 rows, which keeps the 8 stores of a group unpredicated.
                 float* gp = memb + (size_t)(wg * C::CW) * pitch + e;      // row of this warpgroup's first cluster
+                const uint64_t sc2 = pack2f(scale, scale);
 #pragma unroll
                 for (int sg = 0; sg < C::MAXSG; sg++) {
                     if (sg * C::GB + wg * C::CW < K) {
                         float* gq = gp + (size_t)(sg * C::GB) * pitch;
 #pragma unroll
-                        for (int i = 0; i < C::CW; i++) {
-                            *gq = lg[sg * C::CW + i] * scale;             // :498-501
-                            gq += pitch;
+                        for (int u = 0; u < C::CW / 2; u++) {
+                            const uint64_t g2 = fmul2(lgp[sg * C::CW / 2 + u], sc2);      // :498-501
+                            gq[0] = lo2f(g2);
+                            gq[pitch] = hi2f(g2);
+                            gq += 2 * pitch;
                         }
                     }
                 }

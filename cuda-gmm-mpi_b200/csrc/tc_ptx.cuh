@@ -77,6 +77,31 @@ __device__ __forceinline__ float hsum2(uint64_t a, uint64_t b) {   // (a.x + a.y
     return lo + hi;
 }
 
+// packed FP32 pairs (fma / add / mul .f32x2: SASS FFMA2 / FADD2 / FMUL2)
+__device__ __forceinline__ uint64_t pack2u(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t pack2f(float lo, float hi) { return pack2u(__float_as_uint(lo), __float_as_uint(hi)); }
+__device__ __forceinline__ float lo2f(uint64_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi2f(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // ---- proxy fences -----------------------------------------------------------
 // Generic-proxy shared-memory writes -> visible to the async proxy (TMA, tcgen05.mma operands).
 __device__ __forceinline__ void fence_proxy_async_smem() {
