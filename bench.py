@@ -333,6 +333,8 @@ def main():
 
     eng = pkg.Engine(None, Kmax, device=local_rank, n_global=N, offset=begin, events_ptr=ev_pinned.data_ptr(), n_local=count, D=D)
     eng.set_option("path", path)
+    if "GMM_BENCH_ALLREDUCE" in os.environ:              # A/B: 1 = the library's peer-memory kernel (default), 0 = ncclAllReduce
+        eng.set_option("allreduce", int(os.environ["GMM_BENCH_ALLREDUCE"]))
     if world > 1:
         eng.comm_init(world, rank, fresh_nccl_id())
     r_, n_ = eng.comm_rank()

@@ -19,6 +19,7 @@
 #include <functional>
 #include <mutex>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -47,6 +48,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
@@ -65,9 +67,10 @@ static NcclApi& nccl() {
             api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
             api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
             api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+            api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
             api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
             api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
-            api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy && api.GetErrorString;
+            api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.AllGather && api.CommDestroy && api.GetErrorString;
         }
     }
     return api;
@@ -186,6 +189,74 @@ private:
     bool started_ = false;
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// All-reduce of the packed statistics over NVLink peer memory (one box, <= 8 GPUs): replaces the per-iteration
+// ncclAllReduce (and with it the four MPI_Allreduce of gaussian.cu:566,605,658,741) by ONE kernel of this library.
+// Every rank owns an exchange area [2 parities][len doubles] + flags, mapped into every other rank (cudaIpc between
+// processes, peer access between the threads of one process; NCCL only carries the 100-byte handles once, at
+// gmm_comm_init).  Per call and CTA: copy the CTA's chunk of the local statistics into the own area, fence, raise
+// the chunk's flag in every peer (posted remote writes), wait for the G flags of the chunk in LOCAL memory, then sum
+// the chunk over the ranks' areas in rank order (remote loads) — the same order on every rank, so the replicated host
+// finalisation sees bit-identical statistics.  Two parities: a rank can be at most one call ahead of the slowest one.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kXMaxRanks = 8;
+constexpr int kXCtas = 24;                      // chunks of the vector, one CTA each (flags per chunk: no grid barrier)
+struct PeerTable {
+    double* buf[kXMaxRanks];                    // exchange area of rank p as mapped HERE: [2][cap] doubles
+    unsigned long long* flags[kXMaxRanks];      // flags of rank p as mapped here: [2][kXMaxRanks][kXCtas]
+    int nranks, rank;
+    size_t cap;
+};
+struct PeerExchange {
+    PeerTable tab{};
+    void* base = nullptr;                       // own allocation: [2][cap] doubles, then the flags
+    void* opened[kXMaxRanks] = {nullptr};       // cudaIpcOpenMemHandle results to close
+    unsigned long long epoch = 0;
+    bool ok = false;
+};
+struct PeerHello {                              // what every rank tells the others (carried by ncclAllGather once)
+    cudaIpcMemHandle_t handle;
+    unsigned long long ptr;
+    long long pid;
+    int device, ok;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(1024)
+allreduce_peer_kernel(PeerTable t, double* __restrict__ stats, int len, int parity, unsigned long long epoch) {
+    const int per = (len + kXCtas - 1) / kXCtas;
+    const int i0 = blockIdx.x * per, i1 = min(len, i0 + per);
+    double* mine = t.buf[t.rank] + (size_t)parity * t.cap;
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) mine[i] = stats[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < t.nranks)                  // tell rank threadIdx.x that this chunk of rank t.rank is in place
+        st_release_sys(t.flags[threadIdx.x] + ((size_t)parity * kXMaxRanks + t.rank) * kXCtas + blockIdx.x, epoch);
+    if (threadIdx.x < t.nranks) {
+        const unsigned long long* f = t.flags[t.rank] + ((size_t)parity * kXMaxRanks + threadIdx.x) * kXCtas + blockIdx.x;
+        while (ld_acquire_sys(f) < epoch) __nanosleep(20);
+    }
+    __syncthreads();
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        double s = 0.0;
+        for (int p = 0; p < t.nranks; p++) s += ld_relaxed_sys(t.buf[p] + (size_t)parity * t.cap + i);
+        stats[i] = s;
+    }
+}
+
 }  // namespace gmm
 
 using namespace gmm;
@@ -238,6 +309,8 @@ struct gmm_ctx {
     long long iterations = 0;
     TcState* tc = nullptr;       // tensor-core path state (kernels_tc.cuh)
     HostPool* pool = nullptr;    // worker team of the per-iteration host finalisation (created on first use)
+    PeerExchange xchg;           // peer-memory all-reduce of the statistics (gmm_comm_init; falls back to NCCL)
+    int allreduce_mode = 1;      // option "allreduce": 1 = peer-memory kernel when available, 0 = ncclAllReduce
     bool estep_tensor_ready = false;   // the tensor E-step operand of the current parameters is uploaded
 };
 
@@ -474,8 +547,14 @@ static int reduce_stats_to_host(gmm_ctx* c, int K) {
     const size_t len = (size_t)K * c->F + 1;
     timer_begin(c, c->t_reduce);
     if (c->nranks > 1) {
-        ncclResult_t r = nccl().AllReduce(c->d_stats, c->d_stats, len, ncclDouble, ncclSum, c->comm, c->stream);
-        if (r != ncclSuccess) return fail(GMM_ERR_NCCL, std::string("ncclAllReduce: ") + nccl().GetErrorString(r));
+        if (c->xchg.ok && c->allreduce_mode == 1 && len <= c->xchg.tab.cap) {
+            c->xchg.epoch++;
+            allreduce_peer_kernel<<<kXCtas, 1024, 0, c->stream>>>(c->xchg.tab, c->d_stats, (int)len, (int)(c->xchg.epoch & 1), c->xchg.epoch);
+            CUDA_TRY(cudaGetLastError());
+        } else {
+            ncclResult_t r = nccl().AllReduce(c->d_stats, c->d_stats, len, ncclDouble, ncclSum, c->comm, c->stream);
+            if (r != ncclSuccess) return fail(GMM_ERR_NCCL, std::string("ncclAllReduce: ") + nccl().GetErrorString(r));
+        }
     }
     timer_end(c, c->t_reduce);
     CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(double) * len, cudaMemcpyDeviceToHost, c->stream));
@@ -543,6 +622,9 @@ static int check_K(const gmm_ctx* c, int K, const char* who) {
 
 // ===========================================================================
 extern "C" {
+
+static int peer_exchange_setup(gmm_ctx* c);
+static void peer_exchange_destroy(gmm_ctx* c);
 
 const char* gmm_version(void) { return "cuda-gmm-mpi_b200 0.1 (sm_100a)"; }
 
@@ -699,6 +781,7 @@ void gmm_destroy(gmm_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     collect_all(c);
+    peer_exchange_destroy(c);
     if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
     tc_destroy(c->tc);
     delete c->pool;
@@ -710,6 +793,88 @@ void gmm_destroy(gmm_ctx* c) {
     c->events.destroy();
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
+}
+
+// Maps every rank's exchange area into this rank (see allreduce_peer_kernel).  Never fatal: whatever goes wrong on
+// any rank (no peer access, IPC refused, more than 8 ranks) leaves ALL ranks on ncclAllReduce — the decision is itself
+// agreed through the gathered `ok` fields.
+static int peer_exchange_setup(gmm_ctx* c) {
+    PeerExchange& x = c->xchg;
+    x.ok = false;
+    const int G = c->nranks;
+    const size_t cap = (size_t)c->Kmax * c->F + 1;
+    const size_t flag_count = (size_t)2 * kXMaxRanks * kXCtas;
+    const size_t bytes = sizeof(double) * 2 * cap + sizeof(unsigned long long) * flag_count;
+    PeerHello me{};
+    me.pid = (long long)getpid();
+    me.device = c->device;
+    me.ok = (G <= kXMaxRanks && getenv("GMM_NO_PEER_ALLREDUCE") == nullptr) ? 1 : 0;
+    if (me.ok && cudaMalloc(&x.base, bytes) != cudaSuccess) { x.base = nullptr; me.ok = 0; cudaGetLastError(); }
+    if (me.ok) {
+        cudaMemset(x.base, 0, bytes);
+        me.ptr = (unsigned long long)(uintptr_t)x.base;
+        if (cudaIpcGetMemHandle(&me.handle, x.base) != cudaSuccess) { me.ok = 0; cudaGetLastError(); }
+    }
+    // gather the hellos (device staging; NCCL is the only channel the C ABI has between ranks)
+    PeerHello* d_all = nullptr;
+    std::vector<PeerHello> all((size_t)G);
+    CUDA_TRY(cudaMalloc(&d_all, sizeof(PeerHello) * G));
+    CUDA_TRY(cudaMemcpyAsync(d_all + c->rank, &me, sizeof(PeerHello), cudaMemcpyHostToDevice, c->stream));
+    {
+        ncclResult_t r = nccl().AllGather(d_all + c->rank, d_all, sizeof(PeerHello), ncclChar, c->comm, c->stream);
+        if (r != ncclSuccess) { cudaFree(d_all); return fail(GMM_ERR_NCCL, std::string("ncclAllGather: ") + nccl().GetErrorString(r)); }
+    }
+    CUDA_TRY(cudaMemcpyAsync(all.data(), d_all, sizeof(PeerHello) * G, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(d_all);
+    int ok = 1;
+    for (int p = 0; p < G; p++) ok &= all[p].ok;
+    x.tab.nranks = G; x.tab.rank = c->rank; x.tab.cap = cap;
+    for (int p = 0; p < G && ok; p++) {
+        void* mapped = nullptr;
+        if (p == c->rank) mapped = x.base;
+        else if (all[p].pid == me.pid) {                 // a thread of this process: plain peer access
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, c->device, all[p].device) != cudaSuccess || !can) ok = 0;
+            else {
+                cudaError_t e = cudaDeviceEnablePeerAccess(all[p].device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+                cudaGetLastError();
+                mapped = (void*)(uintptr_t)all[p].ptr;
+            }
+        } else {
+            if (cudaIpcOpenMemHandle(&mapped, all[p].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+            else x.opened[p] = mapped;
+        }
+        if (ok) {
+            x.tab.buf[p] = reinterpret_cast<double*>(mapped);
+            x.tab.flags[p] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(mapped) + sizeof(double) * 2 * cap);
+        }
+    }
+    // a rank that failed to map somebody must take everybody back to NCCL: agree on the minimum
+    {
+        double* d_ok = nullptr;
+        double h_ok = ok ? 1.0 : 0.0;
+        CUDA_TRY(cudaMalloc(&d_ok, sizeof(double)));
+        CUDA_TRY(cudaMemcpyAsync(d_ok, &h_ok, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        ncclResult_t r = nccl().AllReduce(d_ok, d_ok, 1, ncclDouble, ncclMin, c->comm, c->stream);
+        if (r != ncclSuccess) { cudaFree(d_ok); return fail(GMM_ERR_NCCL, std::string("ncclAllReduce: ") + nccl().GetErrorString(r)); }
+        CUDA_TRY(cudaMemcpyAsync(&h_ok, d_ok, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        cudaFree(d_ok);
+        ok = h_ok > 0.5;
+    }
+    x.ok = ok != 0;
+    if (c->verbose) std::printf("[gmm rank %d] statistics all-reduce: %s\n", c->rank, x.ok ? "peer-memory kernel (NVLink)" : "ncclAllReduce");
+    return GMM_OK;
+}
+
+static void peer_exchange_destroy(gmm_ctx* c) {
+    PeerExchange& x = c->xchg;
+    for (int p = 0; p < kXMaxRanks; p++)
+        if (x.opened[p]) { cudaIpcCloseMemHandle(x.opened[p]); x.opened[p] = nullptr; }
+    if (x.base) { cudaFree(x.base); x.base = nullptr; }
+    x.ok = false;
 }
 
 int gmm_nccl_unique_id(char id_out[128]) {
@@ -736,7 +901,7 @@ int gmm_comm_init(gmm_ctx* c, int nranks, int rank, const char id_in[128]) {
     ncclUniqueId id;
     std::memcpy(&id, id_in, 128);
     NCCL_TRY(nccl().CommInitRank(&c->comm, nranks, id, rank));
-    return GMM_OK;
+    return peer_exchange_setup(c);
 }
 
 int gmm_comm_rank(const gmm_ctx* c, int* rank, int* nranks) {
@@ -765,6 +930,7 @@ int gmm_set_option(gmm_ctx* c, const char* key, double value) {
         (k == "estep_path" ? c->estep_path : c->mstep_path) = p;
     }
     else if (k == "profile") c->profile_phases = value != 0;
+    else if (k == "allreduce") c->allreduce_mode = value != 0 ? 1 : 0;
     else return fail(GMM_ERR_ARG, "gmm_set_option: unknown key '" + k + "'");
     return GMM_OK;
 }

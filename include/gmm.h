@@ -110,6 +110,9 @@ int  gmm_comm_rank(const gmm_ctx*, int* rank, int* nranks);
  * "path"), "verbose", "host_threads" (threads of the host-side
  * finalisation), "profile" (0 = no per-phase CUDA-event timers inside the EM
  * loop; gmm_get_profile then reports zeros for the device phases),
+ * "allreduce" (1, default = the per-iteration sum of the packed statistics runs
+ * as this library's own kernel over NVLink peer memory when every rank could map
+ * every other rank's exchange area — one box, <= 8 GPUs; 0 = ncclAllReduce),
  * "mstep_gamma_split" (tensor M-step: 1 = responsibilities enter the MMA as
  * an FP16 hi/lo pair, 0 = as one round-to-nearest FP16 value (10 % faster
  * kernel, ~1.4e-4/sqrt(N_k) statistical error per cluster), 2 (default) =

@@ -73,7 +73,7 @@ def test_em_iterations_matches_oracle(loaded, oracle64, path):
         check(eng, ref2, ll_ref2)
 
 
-def _run_sharded(pkg, ev, K, G, iters, path):
+def _run_sharded(pkg, ev, K, G, iters, path, allreduce=1):
     """G contexts (one per GPU, one host thread each) through the C ABI; returns rank 0's clusters with the
     memberships of all shards gathered, the log-likelihood and every rank's parameters."""
     N, D = ev.shape
@@ -85,6 +85,7 @@ def _run_sharded(pkg, ev, K, G, iters, path):
             b, n = pkg.shard_range(N, G, g)
             with pkg.Engine(np.ascontiguousarray(ev[b:b + n]), K, device=g, n_global=N, offset=b) as eng:
                 eng.set_option("path", path)
+                eng.set_option("allreduce", allreduce)
                 eng.comm_init(G, g, uid)
                 eng.seed(K)
                 ll, it = eng.em(K, iters, iters)
@@ -131,6 +132,25 @@ def test_sharded_c_abi_equals_single_gpu_and_oracle(loaded, oracle64, G, path):
     assert abs(llg - ll_ref) <= 1e-5 * abs(ll_ref)
     assert_params_close(many, ref, K, rtol_N=RUN_RTOL_N)
     np.testing.assert_allclose(many.memberships, ref.memberships, **RUN_MEMB)
+
+
+@pytest.mark.parametrize("G", [2, 8])
+def test_peer_memory_allreduce_equals_nccl(loaded, G):
+    """The statistics all-reduce of this library (one kernel over NVLink peer memory, rank-ordered sums) against
+    ncclAllReduce on the same run: the packed statistics are doubles, only the summation order differs."""
+    if gpu_count() < G:
+        pytest.skip(f"needs >= {G} GPUs")
+    pkg = loaded
+    N, D, K, iters = 90_001, 24, 20, 6
+    ev = pkg.synth.make_blobs(N, D, K, seed=72)
+    a, lla, ranks_a = _run_sharded(pkg, ev, K, G, iters, pkg.PATH_AUTO, allreduce=1)
+    b, llb, _ = _run_sharded(pkg, ev, K, G, iters, pkg.PATH_AUTO, allreduce=0)
+    for f in ("N", "pi", "constant", "means", "R", "Rinv"):
+        for r in ranks_a[1:]:
+            np.testing.assert_array_equal(getattr(r, f)[:K], getattr(ranks_a[0], f)[:K], err_msg=f"rank-divergent {f}")
+    assert abs(lla - llb) <= 1e-6 * abs(llb)
+    assert_params_close(a, b, K, rtol=1e-6)
+    np.testing.assert_allclose(a.memberships, b.memberships, rtol=1e-5, atol=1e-7)
 
 
 @pytest.mark.parametrize("path", ["simt", "auto"])
