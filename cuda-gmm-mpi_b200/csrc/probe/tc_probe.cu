@@ -100,6 +100,61 @@ __global__ void __launch_bounds__(128, 1) probe_mma_kernel(ProbeArgs p) {
     if (threadIdx.x < 32) tmem_dealloc<512>(tmem);
 }
 
+// T9: A operand from TENSOR MEMORY (tcgen05.mma ... [d], [a_tmem], b_desc): every thread = one row of A writes its K/2
+// packed FP16 pairs with tcgen05.st, then one thread issues the k-steps.  repeats > 1: throughput (cycles per MMA) with
+// the B operand in shared memory only — against 64 cycles for the smem-smem form at N = 128.
+struct ProbeTsArgs { const uint32_t* a_pairs; const uint8_t* b_img; int b_bytes, b_lbo, b_sbo, b_kstep_bytes, N, ksteps, repeats; float* d_out; long long* cycles; };
+__global__ void __launch_bounds__(128, 1) probe_mma_ts_kernel(ProbeTsArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    for (int i = threadIdx.x * 16; i < p.b_bytes; i += blockDim.x * 16) *(uint4*)(smem + i) = *(const uint4*)(p.b_img + i);
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (threadIdx.x < 32) tmem_alloc<512>(&tmem_base_s);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t ACOL = 256;
+    {   // row = thread: 8 columns per k-step
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        for (int k = 0; k < p.ksteps; k++) {
+            uint32_t v[8];
+            for (int j = 0; j < 8; j++) v[j] = p.a_pairs[(size_t)(warp * 32 + lane) * (p.ksteps * 8) + k * 8 + j];
+            tmem_st_32x8(tmem + lane_base + ACOL + k * 8, v);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_f16(128, p.N, false, false);
+        long long t0 = clock64();
+        for (int r = 0; r < p.repeats; r++)
+            for (int k = 0; k < p.ksteps; k++) {
+                uint64_t bd = make_smem_desc(smem_u32(smem) + k * p.b_kstep_bytes, p.b_lbo, p.b_sbo);
+                mma_f16_ts(tmem, tmem + ACOL + k * 8, bd, idesc, (r | k) != 0);
+            }
+        mma_commit(&bar);
+        mbar_wait(&bar, 0);
+        if (p.cycles) p.cycles[0] = clock64() - t0;
+    }
+    __syncthreads();
+    tc_fence_after();
+    for (int c0 = 0; c0 < p.N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
+        tmem_ld_wait();
+        for (int j = 0; j < 32 && c0 + j < p.N; j++) p.d_out[(size_t)(warp * 32 + lane) * p.N + c0 + j] = __uint_as_float(r[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc<512>(tmem);
+}
+
 // T4: TMEM load throughput
 __global__ void __launch_bounds__(128, 1) probe_ld_kernel(int iters, long long* cycles, float* sink) {
     __shared__ uint32_t tmem_base_s;
@@ -441,6 +496,45 @@ int main() {
             printf("T8 %d-bit operands, %3d k-steps (sum needs <= %d bits): max|err| = %g product quanta\n", bits, repeats,
                    2 * bits + 4 + (repeats == 8 ? 3 : 7), maxerr);
         }
+    }
+    // ---- T9: A operand from tensor memory ----
+    for (int repeats : {1, 2048}) {
+        const int N = 128, K = 64;
+        std::vector<float> A((size_t)128 * K), B((size_t)N * K);
+        for (auto& v : A) v = repeats == 1 ? (float)(rand() % 9 - 4) : 1.0f;
+        for (auto& v : B) v = repeats == 1 ? (float)(rand() % 7 - 3) : 1.0f;
+        std::vector<uint32_t> ap((size_t)128 * K / 2);
+        for (int m = 0; m < 128; m++)
+            for (int k = 0; k < K; k += 2) {
+                __half lo = __float2half_rn(A[(size_t)m * K + k]), hi = __float2half_rn(A[(size_t)m * K + k + 1]);
+                ap[(size_t)m * (K / 2) + k / 2] = (uint32_t)(*(unsigned short*)&lo) | ((uint32_t)(*(unsigned short*)&hi) << 16);
+            }
+        int blbo, bsbo;
+        std::vector<uint8_t> bi = build_kmajor(B, N, K, blbo, bsbo);
+        uint32_t* da; uint8_t* db; float* dout; long long* dcyc;
+        CK(cudaMalloc(&da, ap.size() * 4)); CK(cudaMalloc(&db, bi.size())); CK(cudaMalloc(&dout, sizeof(float) * 128 * N)); CK(cudaMalloc(&dcyc, 8));
+        CK(cudaMemcpy(da, ap.data(), ap.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(db, bi.data(), bi.size(), cudaMemcpyHostToDevice));
+        ProbeTsArgs p{da, db, (int)bi.size(), blbo, bsbo, 2 * blbo, N, K / 16, repeats, dout, dcyc};
+        size_t smem = bi.size() + 1024;
+        CK(cudaFuncSetAttribute(probe_mma_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        probe_mma_ts_kernel<<<1, 128, smem>>>(p);
+        CK(cudaDeviceSynchronize());
+        std::vector<float> Dv((size_t)128 * N);
+        long long cyc;
+        CK(cudaMemcpy(Dv.data(), dout, sizeof(float) * 128 * N, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost));
+        if (repeats == 1) {
+            double maxerr = 0;
+            for (int m = 0; m < 128; m++)
+                for (int n = 0; n < N; n++) {
+                    double ref = 0;
+                    for (int k = 0; k < K; k++) ref += (double)A[(size_t)m * K + k] * B[(size_t)n * K + k];
+                    maxerr = fmax(maxerr, fabs(ref - Dv[(size_t)m * N + n]));
+                }
+            printf("T9 A operand from TMEM (tcgen05.st rows, 8 columns per k-step), N=%d K=%d: max|err| = %g  %s\n", N, K, maxerr, maxerr == 0 ? "PASS" : "FAIL");
+        } else {
+            printf("T9 A from TMEM, M=128 N=%d K=16 fp16: %.1f cycles per MMA (A and B from shared memory: 64.1)\n", N, (double)cyc / (2048.0 * (K / 16)));
+        }
+        cudaFree(da); cudaFree(db); cudaFree(dout); cudaFree(dcyc);
     }
     // ---- T3: MMA throughput (single CTA) ----
     for (int N : {64, 192, 256}) {
