@@ -245,15 +245,22 @@ allreduce_peer_kernel(PeerTable t, double* __restrict__ stats, int len, int pari
     __syncthreads();
     if (threadIdx.x < t.nranks)                  // tell rank threadIdx.x that this chunk of rank t.rank is in place
         st_release_sys(t.flags[threadIdx.x] + ((size_t)parity * kXMaxRanks + t.rank) * kXCtas + blockIdx.x, epoch);
+    __shared__ int timed_out;
+    if (threadIdx.x == 0) timed_out = 0;
+    __syncthreads();
     if (threadIdx.x < t.nranks) {
         const unsigned long long* f = t.flags[t.rank] + ((size_t)parity * kXMaxRanks + threadIdx.x) * kXCtas + blockIdx.x;
-        while (ld_acquire_sys(f) < epoch) __nanosleep(20);
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < epoch) {
+            __nanosleep(20);
+            if (clock64() - t0 > 20000000000LL) { timed_out = 1; break; }      // ~10 s: a peer is gone; do not hang the GPU
+        }
     }
     __syncthreads();
     for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
         double s = 0.0;
         for (int p = 0; p < t.nranks; p++) s += ld_relaxed_sys(t.buf[p] + (size_t)parity * t.cap + i);
-        stats[i] = s;
+        stats[i] = timed_out ? __longlong_as_double(0x7ff8000000000000LL) : s;   // NaN: the host reports the failure
     }
 }
 
@@ -406,10 +413,9 @@ static int upload_params(gmm_ctx* c, int K, bool with_constants = false, bool wi
             if (with_constants) mixing_weights(K, &c->host);
             const int kp = tc_params_padded(c->tc, K), D = c->D;
             std::atomic<int> bad_all{0};
-            const int nt = K >= 8 ? c->host_threads : 1;
-            if (!c->pool) c->pool = new HostPool(nt);
-            else c->pool->resize(nt);
-            c->pool->run(kp, [&](int k) {
+            if (!c->pool) c->pool = new HostPool(c->host_threads);
+            else c->pool->resize(c->host_threads);
+            const std::function<void(int)> per_cluster = [&](int k) {
                 if (with_finalize && k < K) finalize_cluster(c->h_stats, c->shift, k, D, &c->host);
                 int b;
                 double W[GMM_MAX_DIMENSIONS * GMM_MAX_DIMENSIONS];
@@ -421,7 +427,9 @@ static int upload_params(gmm_ctx* c, int K, bool with_constants = false, bool wi
                 }
                 int cur = bad_all.load(std::memory_order_relaxed);
                 while (b > cur && !bad_all.compare_exchange_weak(cur, b)) {}
-            });
+            };
+            if (K >= 8) c->pool->run(kp, per_cluster);
+            else for (int k = 0; k < kp; k++) per_cluster(k);
             const int bad = bad_all.load();
             with_constants = with_finalize = false;
             rc = tc_params_commit(c->tc, K, bad, c->stream);
@@ -560,6 +568,8 @@ static int reduce_stats_to_host(gmm_ctx* c, int K) {
     CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(double) * len, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaEventRecord(c->ev_stats, c->stream));
     CUDA_TRY(cudaEventSynchronize(c->ev_stats));
+    if (c->nranks > 1 && std::isnan(c->h_stats[0]))
+        return fail(GMM_ERR_NCCL, "statistics all-reduce failed (a rank did not arrive, or a cluster's statistics are not finite)");
     return GMM_OK;
 }
 
@@ -1189,7 +1199,10 @@ int gmm_fit(gmm_ctx* c, int K0, int target_K, int min_iters, int max_iters, clus
         }
         if (K > stop_number) {                                            // :860-950
             const auto t0 = now();
-            K = reduce_order(&c->host, K, D, nullptr, nullptr, c->host_threads);
+            if (!c->pool) c->pool = new HostPool(c->host_threads);
+            else c->pool->resize(c->host_threads);
+            const ParallelFor pfor = [&](int n, const std::function<void(int)>& fn) { c->pool->run(n, fn); };
+            K = reduce_order(&c->host, K, D, nullptr, nullptr, c->host_threads, &pfor);
             c->fit_reduce_ms += ms_since(t0);
             if (K < 1) break;
             c->memb_valid = false;

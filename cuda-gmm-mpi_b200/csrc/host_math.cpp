@@ -260,7 +260,7 @@ void move_cluster(clusters_t* c, int dst, int src, int D) {               // cop
 }
 }  // namespace
 
-int reduce_order(clusters_t* c, int K, int D, int* out_c1, int* out_c2, int num_threads) {
+int reduce_order(clusters_t* c, int K, int D, int* out_c1, int* out_c2, int num_threads, const ParallelFor* pfor) {
     (void)num_threads;
     for (int i = K - 1; i >= 0; i--)                                      // empties :866-874
         if (c->N[i] < 0.5f) {
@@ -271,14 +271,20 @@ int reduce_order(clusters_t* c, int K, int D, int* out_c1, int* out_c2, int num_
     if (K >= 2) {
         const int npairs = K * (K - 1) / 2;
         std::vector<float> dist(npairs);
-#pragma omp parallel for schedule(dynamic, 16) num_threads(num_threads) if (npairs >= 64 && num_threads > 1)
-        for (int p = 0; p < npairs; p++) {
+        auto one_pair = [&](int p) {
             int a = 0, rem = p;                                           // p -> (a, b), a < b, row-major
             while (rem >= K - 1 - a) { rem -= K - 1 - a; a++; }
             const int b = a + 1 + rem;
             Merged m;
             merge_pair(c, a, b, D, m);
             dist[p] = c->N[a] * c->constant[a] + c->N[b] * c->constant[b] - m.N * m.constant;
+        };
+        if (pfor && *pfor && npairs >= 64) {                              // the caller's worker team, 16 pairs per task
+            const int ntask = (npairs + 15) / 16;
+            (*pfor)(ntask, [&](int t) { for (int p = t * 16; p < npairs && p < t * 16 + 16; p++) one_pair(p); });
+        } else {
+#pragma omp parallel for schedule(dynamic, 16) num_threads(num_threads) if (npairs >= 64 && num_threads > 1)
+            for (int p = 0; p < npairs; p++) one_pair(p);
         }
         float best = 0.0f;
         int p = 0;

@@ -2,6 +2,7 @@
 // The extern "C" wrappers of include/gmm.h live in host_math.cpp.
 #pragma once
 #include <cstddef>
+#include <functional>
 #include <string>
 #include <vector>
 #include "../../include/gmm.h"
@@ -49,8 +50,10 @@ long long seed_event_index(int c, int K, long long N);
 float rissanen(float loglik, int K, int D, long long N);
 float em_epsilon(int D, long long N);
 
-// One order-reduction step (gaussian.cu:860-907).  Returns new K.
-int reduce_order(clusters_t* c, int K, int D, int* c1, int* c2, int num_threads);
+// One order-reduction step (gaussian.cu:860-907).  Returns new K.  The K(K-1)/2 trial merges run on the caller's
+// worker team when `pfor` is given (pfor(n, fn) calls fn(0..n-1) in parallel), else on an OpenMP team of num_threads.
+using ParallelFor = std::function<void(int, const std::function<void(int)>&)>;
+int reduce_order(clusters_t* c, int K, int D, int* c1, int* c2, int num_threads, const ParallelFor* pfor = nullptr);
 
 // Packed E-step parameters for the SIMT kernel: per cluster
 //   [ mean(D) | c_ii, 2c_ij (j>i) row by row (D(D+1)/2) | constant + ln(pi) ] padded to stride.
