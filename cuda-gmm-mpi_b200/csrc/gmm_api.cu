@@ -121,11 +121,14 @@ public:
     void run(int n, const std::function<void(int)>& fn) {
         if (n <= 0) return;
         if (workers_.empty() || n == 1) { for (int i = 0; i < n; i++) fn(i); return; }
-        // a worker may still be on its way out of the previous job's loop: everything it could read is published
-        // before `next_` restarts (release), and the completion count is reset before any new item can be taken
+        // Items are claimed by counting `remaining_` DOWN: a claim is valid iff the value it saw was positive, so a worker
+        // still on its way out of the previous job's loop either sees <= 0 (before the store below) or a genuine item of
+        // THIS job (after it) — there is no window in which a stale claim can be mistaken for a new one (an index
+        // counted up against a separately published bound had one: found by gmm_host_pool_selftest).  Everything a
+        // claimer reads is published before the store (release / acquire on `remaining_`).
         fn_ = &fn; n_ = n;
         done_.store(0, std::memory_order_relaxed);
-        next_.store(0, std::memory_order_release);
+        remaining_.store(n, std::memory_order_release);
         {
             std::lock_guard<std::mutex> lk(m_);
             gen_.fetch_add(1, std::memory_order_release);
@@ -142,9 +145,9 @@ private:
     }
     void work() {
         for (;;) {
-            const int i = next_.fetch_add(1, std::memory_order_acq_rel);
-            if (i >= n_) break;
-            (*fn_)(i);
+            const int r = remaining_.fetch_sub(1, std::memory_order_acq_rel);
+            if (r <= 0) break;
+            (*fn_)(r - 1);
             done_.fetch_add(1, std::memory_order_release);
         }
     }
@@ -182,7 +185,7 @@ private:
     std::mutex m_;
     std::condition_variable cv_;
     std::atomic<unsigned long long> gen_{0};
-    std::atomic<int> next_{0}, done_{0};
+    std::atomic<int> remaining_{0}, done_{0};
     std::atomic<bool> quit_{false};
     const std::function<void(int)>* fn_ = nullptr;
     int n_ = 0;
@@ -1150,6 +1153,27 @@ int gmm_get_profile(gmm_ctx* c, double out[8], int reset) {
         c->host_const_ms = c->memcpy_ms = 0; c->iterations = 0;
         c->mstep_tensor = c->mstep_simt = 0;
         c->fit_reduce_ms = c->fit_seed_ms = c->fit_save_ms = 0;
+    }
+    return GMM_OK;
+}
+
+// Host-only self-test of the worker team used by the per-iteration finalisation (tests/test_host.py): `jobs` back-to-back
+// parallel loops of n items on `threads` threads, every item must run exactly once per job.  Returns 0 when it did.
+int gmm_host_pool_selftest(int threads, int jobs, int n) {
+    if (threads < 1 || jobs < 1 || n < 0) return fail(GMM_ERR_ARG, "gmm_host_pool_selftest: bad argument");
+    HostPool pool(threads);
+    std::vector<std::atomic<int>> hits((size_t)(n > 0 ? n : 1));
+    for (auto& h : hits) h.store(0);
+    for (int j = 0; j < jobs; j++) {
+        const int m = (j % 3 == 0) ? n : (j % 3 == 1 ? (n + 1) / 2 : 1);
+        const std::function<void(int)> fn = [&](int i) { hits[(size_t)i].fetch_add(1, std::memory_order_relaxed); };
+        pool.run(m, fn);
+        for (int i = 0; i < n; i++) {
+            const int want = i < m ? 1 : 0;
+            if (hits[(size_t)i].exchange(0) != want) return fail(GMM_ERR_STATE, "gmm_host_pool_selftest: an item ran the wrong number of times");
+        }
+        if (j % 64 == 63) pool.resize(1 + (j / 64) % threads);          // exercise team re-creation as well
+        if (j % 200 == 199) std::this_thread::sleep_for(std::chrono::milliseconds(6));   // let the workers fall asleep once in a while
     }
     return GMM_OK;
 }

@@ -78,6 +78,7 @@ def load_library():
     L.gmm_get_profile.argtypes = [C.c_void_p, _DP, C.c_int]
     L.gmm_get_fit_profile.argtypes = [C.c_void_p, _DP]
     L.gmm_fit.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _CP, _IP, _FP]
+    L.gmm_host_pool_selftest.argtypes = [C.c_int, C.c_int, C.c_int]
     L.gmm_host_invert.argtypes = [_FP, C.c_int, _FP, C.c_int]
     L.gmm_stats_len.argtypes = [C.c_int, C.c_int]
     L.gmm_stats_len.restype = C.c_longlong

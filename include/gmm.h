@@ -204,6 +204,11 @@ long long gmm_stats_len(int K, int D);
 int  gmm_host_finalize(const double* stats, const double* shift, int K, int D,
                        clusters_t* inout);
 
+/* Self-test of the host worker team behind the per-iteration finalisation
+ * (`jobs` parallel loops of n items on `threads` threads); 0 = every item
+ * ran exactly once per loop.                                                 */
+int  gmm_host_pool_selftest(int threads, int jobs, int n);
+
 /* Rissanen / MDL score (gaussian.cu:826) and convergence epsilon (:458).   */
 float gmm_host_rissanen(float loglik, int K, int D, long long N);
 float gmm_host_epsilon(int D, long long N);

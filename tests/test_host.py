@@ -249,3 +249,11 @@ def test_results_writer_matches_printf(pkg, tmp_path):
     for i in range(N):
         exp = ",".join("%f" % float(v) for v in ev[i]) + "\t" + ",".join("%f" % float(v) for v in cl.memberships[:, i])
         assert lines[i] == exp, i
+
+
+def test_host_worker_team_selftest(pkg):
+    """The persistent worker team of the per-iteration host finalisation: thousands of back-to-back parallel loops of
+    varying size (and team re-creation, and sleeping workers) — every item exactly once, no lost wake-up, no deadlock."""
+    lib = pkg.load_library()
+    for threads, jobs, n in ((1, 50, 7), (2, 3000, 64), (8, 3000, 80), (16, 1500, 5)):
+        assert lib.gmm_host_pool_selftest(threads, jobs, n) == 0, lib.gmm_last_error()
