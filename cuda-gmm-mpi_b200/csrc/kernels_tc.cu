@@ -541,12 +541,6 @@ template <int D> struct ECfg {
     static_assert(QCOL + 2 * 64 <= 512, "TMEM columns");
 };
 
-// GMM_ESTEP_EXP (build-time, timing experiments only — results are wrong): 1 = no responsibility stores, 2 = the
-// log-sum-exp stage only drains q, 3 = the squares stage skips the fma.f32x2 work.  Isolates the cost of each stage.
-#ifndef GMM_ESTEP_EXP
-#define GMM_ESTEP_EXP 0
-#endif
-
 template <int D>
 __global__ void __launch_bounds__(768, 1)
 estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_img, const float* __restrict__ ck,
@@ -729,7 +723,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                         if (lane == 0) mbar_arrive(&acc_empty[buf]);   // the block is in registers: hand the buffer back
                         buf = buf + 1 == C::NBUF ? 0 : buf + 1;
 #pragma unroll
-                        for (int i = 0; i < (GMM_ESTEP_EXP == 3 ? 1 : C::CW); i++) {
+                        for (int i = 0; i < C::CW; i++) {
                             sq_acc2(qa[i], v[i * 8 + 0], v[i * 8 + 1]);
                             sq_acc2(qb[i], v[i * 8 + 2], v[i * 8 + 3]);
                             sq_acc2(qa[i], v[i * 8 + 4], v[i * 8 + 5]);
@@ -836,7 +830,7 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
                 }
                 if (wg == 0 && e < n && (mode == 0 || mode == 2)) ll_acc += (double)denom;
             }
-            if (e < n && mode != 1 && (GMM_ESTEP_EXP != 1 || scale == 12345.678f)) {
+            if (e < n && mode != 1) {
                 // Rows [K, 8*ceil(K/8)) are written too (zeros of the padding clusters): the buffer is allocated in
                 // multiples of 8 rows, which keeps the 8 stores of a group unpredicated.
                 float* gp = memb + (size_t)(wg * C::CW) * pitch + e;      // row of this warpgroup's first cluster
