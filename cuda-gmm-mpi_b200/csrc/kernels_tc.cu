@@ -518,7 +518,7 @@ template <int D> struct ECfg {
     static_assert(D % 8 == 0, "tensor E-step: D must be a multiple of 8");
     static constexpr int CP = D / 8;                          // 8-wide chunks of z / blocks of output columns
     static constexpr int NLO = (CP + 1 + 1) / 2 * 2;          // chunks of the [zh | ones (| pad)] x [Wl | v] part
-    static constexpr int NCHKA = 2 * CP + NLO;                // A image chunks: (zh_c, zl_c) pairs, then zh.., ones, pad
+    static constexpr int NCHKA = 2 * CP + 2;                  // A image chunks: (zh_c, zl_c) pairs, then the constant chunks ones, zero
     static constexpr int NCHKB = CP + NLO;                    // B image chunks: Wh_c, then Wl.., v, pad
     static constexpr int GB = 16;                             // clusters per supergroup
     static constexpr int N = GB * 8;                          // MMA N = one block of a supergroup (128 columns)
@@ -587,6 +587,16 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
     // power-of-two scale_k keeps the FP16 whitening factors in range whatever the cluster's width, see bimg_cluster)
     if (threadIdx.x < 64) { ck_s[threadIdx.x] = ck[threadIdx.x] * 1.4426950408889634f; ck_s[64 + threadIdx.x] = ck[64 + threadIdx.x]; }
     if (threadIdx.x < D) { sh_s[threadIdx.x] = shift_f[threadIdx.x]; isc_s[threadIdx.x] = inv_scale_f[threadIdx.x]; }
+    if (threadIdx.x >= 128 && threadIdx.x < 256) {             // constant chunks of both A stages: {1, 1, 0 ...} and zeros
+        const int row = threadIdx.x - 128;
+#pragma unroll
+        for (int st = 0; st < 2; st++) {
+            uint8_t* a = smem + C::OFF_A + st * C::A_STAGE + row * 16;
+            *reinterpret_cast<uint4*>(a + (2 * C::CP) * 2048) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(a + (2 * C::CP + 1) * 2048) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        fence_proxy_async_smem();
+    }
     __syncthreads();
     if (threadIdx.x == 0) {                    // resident B operand: one TMA bulk copy per block
         mbar_arrive_expect_tx(b_full, (uint32_t)NSG * C::B_SG);
@@ -631,7 +641,12 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
 #pragma unroll
                         for (int t = 0; t < C::NLO / 2; t++) {  // (zh.., ones) x (Wl.., v): needed iff it holds a chunk index >= c
                             if (2 * t + 1 >= c) {
-                                const uint64_t adesc = make_smem_desc(abase + (2 * C::CP + 2 * t) * 2048, /*LBO*/ 2048, /*SBO*/ 128);
+                                // A side of this step: elements 2t and 2t+1 of [zh_0 .. zh_{CP-1}, ones, zero] — zh_m is the chunk the
+                                // (zh_m, zl_m) steps already use (chunk 2m), so the step's two K chunks are simply further apart
+                                constexpr int CP_ = C::CP;
+                                const int m0 = 2 * t, m1 = 2 * t + 1;
+                                const int ch0 = m0 < CP_ ? 2 * m0 : 2 * CP_ + (m0 - CP_), ch1 = m1 < CP_ ? 2 * m1 : 2 * CP_ + (m1 - CP_);
+                                const uint64_t adesc = make_smem_desc(abase + ch0 * 2048, /*LBO*/ (uint32_t)(ch1 - ch0) * 2048, /*SBO*/ 128);
                                 const uint64_t bdesc = make_smem_desc(bbase + (C::CP + 2 * t) * (C::N * 16), /*LBO*/ C::N * 16, /*SBO*/ 128);
                                 mma_f16_ss(tmem + buf * C::N, adesc, bdesc, idesc, acc);
                                 acc = true;
@@ -678,15 +693,12 @@ estep_tc_kernel(const float* __restrict__ x_aos, const uint8_t* __restrict__ b_i
             mbar_wait_parked(&a_empty[st], ph ^ 1, 1000);
             uint8_t* a = smem + C::OFF_A + st * C::A_STAGE + row * 16;     // K-major: [chunk][row][16 B]
 #pragma unroll
-            for (int c = 0; c < C::CP; c++) {
+            for (int c = 0; c < C::CP; c++) {                  // the constant chunks (ones, zero) were written once at kernel start
                 const uint4 h = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
                 const uint4 l = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
                 *reinterpret_cast<uint4*>(a + (2 * c) * 2048) = h;
                 *reinterpret_cast<uint4*>(a + (2 * c + 1) * 2048) = l;
-                *reinterpret_cast<uint4*>(a + (2 * C::CP + c) * 2048) = h;
             }
-            *reinterpret_cast<uint4*>(a + (3 * C::CP) * 2048) = make_uint4(0x3C003C00u, 0u, 0u, 0u);      // {1, 1, 0...}
-            if (C::NLO > C::CP + 1) *reinterpret_cast<uint4*>(a + (3 * C::CP + 1) * 2048) = make_uint4(0u, 0u, 0u, 0u);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[st]);

@@ -1,6 +1,7 @@
+# the round-end sequence on one GPU: full GPU suite, smoke(), default bench.py, reference arm
 set -x
 mkdir -p gpurun_out
-timeout 500 python -m pytest tests -m gpu -q > gpurun_out/pytest_validate.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_validate.log
+timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/pytest_validate.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_validate.log
 timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
-timeout 300 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?" >> gpurun_out/bench_default.err
+timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?" >> gpurun_out/bench_default.err
 echo done

@@ -485,6 +485,30 @@ def test_cli_end_to_end(loaded, oracle64, tmp_path):
     np.testing.assert_allclose(m, s.memberships[:3, 17], atol=2e-4)
 
 
+def test_cli_csv_input_equals_bin(loaded, tmp_path):
+    """The CLI's two input routes — `.bin` streamed from the file to the device shard by shard, anything else parsed as
+    comma-separated text with one header line into host memory (readData.cpp:49-129) — give the same output files."""
+    pkg = loaded
+    exe = os.path.join(ROOT, "cuda-gmm-mpi_b200", "gaussianMPI_b200")
+    N, D, K0 = 3_000, 4, 4
+    ev = pkg.synth.make_blobs(N, D, 3, seed=16)
+    # values that survive the text round trip exactly (atof of %.9g is the same float)
+    pkg.synth.write_bin(str(tmp_path / "d.bin"), ev)
+    with open(tmp_path / "d.csv", "w") as f:
+        f.write(",".join(f"col{i}" for i in range(D)) + "\n")
+        for row in ev:
+            f.write(",".join("%.9g" % float(v) for v in row) + "\n")
+    env = dict(os.environ, GMM_ITERS="8", GMM_GPUS="1")
+    outs = []
+    for name in ("d.bin", "d.csv"):
+        r = subprocess.run([exe, str(K0), str(tmp_path / name), str(tmp_path / ("out_" + name)), "3"], capture_output=True, text=True,
+                           env=env, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append((open(str(tmp_path / ("out_" + name)) + ".summary").read(), open(str(tmp_path / ("out_" + name)) + ".results").read()))
+    assert outs[0][0] == outs[1][0]
+    assert outs[0][1] == outs[1][1]
+
+
 @pytest.mark.skipif(gpu_count() < 2, reason="needs >= 2 GPUs")
 def test_cli_two_gpus_equals_one(loaded, tmp_path):
     """Sharded run == single-GPU run (one NCCL all-reduce of the packed statistics)."""
