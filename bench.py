@@ -391,10 +391,14 @@ def main():
         dt_e2e = float(np.median(e2e_times))
         F = 1 + D + D * (D + 1) // 2
         params_bytes = 4 * K * (4 + D + 2 * D * D)
-        upload_bytes = 4 * K * (D + D * (D + 1) // 2 + 8)      # packed E-step operand per iteration
+        # host finalisation: the reduced statistics come to the host and the packed E-step operand goes back every iteration;
+        # device finalisation (option "finalize", the default): neither — parameters and log-likelihood once per batch
+        dev_fin_e2e = eng.fit_profile().get("device_finalize_launches", 0) > 0
+        upload_bytes = 0 if dev_fin_e2e else 4 * K * (D + D * (D + 1) // 2 + 8)
+        stats_bytes = 0 if dev_fin_e2e else 8 * (K * F + 1)
         e2e = dict(value=args.steps / dt_e2e, unit="it/s",
                    h2d_bytes_per_step=int((count * D * 4 + params_bytes) / args.steps + upload_bytes),
-                   d2h_bytes_per_step=int(8 * (K * F + 1) + params_bytes / args.steps),
+                   d2h_bytes_per_step=int(stats_bytes + (params_bytes + 8) / args.steps),
                    iterations_per_upload=args.steps, all_its=[args.steps / t for t in e2e_times],
                    note=f"median of 3; each measurement = ONE gmm_upload_events (pinned H2D of the {count}x{D} shard) + gmm_set_clusters + "
                         f"gmm_estep + {args.steps} iterations + gmm_get_clusters (D2H): {args.steps} iterations per upload, per-step bytes "
@@ -410,7 +414,8 @@ def main():
     e_gbs = e_bytes / (estep_ms * 1e-3) / 1e9 if estep_ms > 0 else 0.0
     m_tfs = m_flops / (mstep_ms * 1e-3) / 1e12 if mstep_ms > 0 else 0.0
     tensor_m = args.path != "simt" and D in (4, 8, 12, 16, 20, 24)
-    launches_per_step = 3 if tensor_m else 2
+    dev_fin = eng.fit_profile().get("device_finalize_launches", 0) > 0
+    launches_per_step = (3 if tensor_m else 2) + (1 if dev_fin else 0)     # E-step, M-step (+ its reduction), finalize_params_kernel
     n_tensor, n_simt = int(prof.get("mstep_tensor_launches", 0)), int(prof.get("mstep_simt_launches", 0))
     F = 1 + D + D * (D + 1) // 2
     mt_rows = (F + 127) // 128 * 128
@@ -481,8 +486,9 @@ def main():
                 config=dict(workload=f"{args.workload}: N={N} D={D} K={K} Gaussian blobs (seed {pkg.synth.SEED}), "
                                      f"{count} events on rank 0", path=args.path, l2="inputs (X 0.96 GB + memberships 2.56 GB at c3) exceed the 126 MB L2",
                             parallelism=f"dp{world} (events sharded, one all-reduce of {8 * (K * (1 + D + D * (D + 1) // 2) + 1)} B per step)",
+                            finalisation=("device (finalize_params_kernel, timed under 'upload')" if dev_fin else "host"),
                             arithmetic=("fp32 data and results; tensor path: fp16 hi/lo split operands, fp32 TMEM accumulation, fp64 "
-                                        "statistics reduction and host finalisation" if args.path != "simt" else
+                                        "statistics reduction and finalisation" if args.path != "simt" else
                                         "fp32 E-step, fp64 M-step statistics and host finalisation"),
                             timing=f"median of {len(blocks)} timed blocks of {args.steps} steps each"),
                 clocks=clocks, e2e=e2e, gpu_launches=launches_per_step * args.steps, roofline=roofline, roofline_mstep=roofline_mstep,

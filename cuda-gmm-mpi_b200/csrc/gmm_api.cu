@@ -222,6 +222,7 @@ struct PeerHello {                              // what every rank tells the oth
     unsigned long long ptr;
     long long pid;
     int device, ok;
+    int dev_fin, pad;                           // this rank can finalise on the device (it has events and the buffers)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -322,6 +323,19 @@ struct gmm_ctx {
     PeerExchange xchg;           // peer-memory all-reduce of the statistics (gmm_comm_init; falls back to NCCL)
     int allreduce_mode = 1;      // option "allreduce": 1 = peer-memory kernel when available, 0 = ncclAllReduce
     bool estep_tensor_ready = false;   // the tensor E-step operand of the current parameters is uploaded
+    // device-side finalisation (kernels_tc.cu: finalize_params_kernel): EM iterations without a host round trip
+    int finalize_mode = 1;       // option "finalize": 1 = on the device when the tensor E-step serves the state, 0 = host
+    bool dev_fin_failed = false; // a cluster needed the host path once: this context stays on it
+    bool dev_fin_agreed = true;  // every rank of the communicator can (gmm_comm_init): the replay re-issues collectives
+    float* d_pset[2] = {nullptr, nullptr};   // parameter sets written by the kernel (iteration parity)
+    float* h_pset = nullptr;     // pinned staging of one set
+    float* d_avgvar = nullptr;   // [Kmax]
+    int* d_bad = nullptr;        // [2] first failed iteration (-1), code
+    double* d_llprev = nullptr;  // [2] log-likelihood slot seen by the finalisation of iteration parity
+    char* h_small = nullptr;     // pinned: int bad[2] | double ll[2] | float avgvar[Kmax]
+    PhaseTimer t_final;
+    long long dev_finalize_launches = 0, dev_replays = 0;
+    int fin_fault_iter = -1;     // option "finalize_fault_iter" (tests): that iteration of the next batch reports a failure
 };
 
 namespace gmm {
@@ -346,6 +360,7 @@ static void timer_collect(gmm_ctx* c, PhaseTimer& t) {          // call after a 
 }
 static void collect_all(gmm_ctx* c) {
     timer_collect(c, c->t_estep); timer_collect(c, c->t_mstep); timer_collect(c, c->t_reduce); timer_collect(c, c->t_fused);
+    timer_collect(c, c->t_final);
 }
 
 static void bind_host(gmm_ctx* c) {
@@ -404,6 +419,7 @@ static int ensure_moments(gmm_ctx* c);
 static int upload_params(gmm_ctx* c, int K, bool with_constants = false, bool with_finalize = false) {
     if (int rc = check_path(c, K)) return rc;
     auto t0 = std::chrono::steady_clock::now();
+    const bool from_outside = !with_finalize;          // seed / set_clusters / order reduction: avgvar may have changed
     c->estep_tensor_ready = false;
     if (use_tensor_estep(c, K)) {
         if (int rc = ensure_moments(c)) return rc;
@@ -448,6 +464,11 @@ static int upload_params(gmm_ctx* c, int K, bool with_constants = false, bool wi
         build_epack(K, c->D, &c->host, c->h_epack);
         CUDA_TRY(cudaMemcpyAsync(c->d_epack, c->h_epack, sizeof(float) * (size_t)K * epack_stride(c->D),
                                  cudaMemcpyHostToDevice, c->stream));
+    }
+    if (c->d_avgvar && c->estep_tensor_ready && from_outside) {   // the device-side finalisation adds avgvar to the diagonals
+        float* stage = reinterpret_cast<float*>(c->h_small + 32);
+        std::memcpy(stage, c->host.avgvar, sizeof(float) * (size_t)K);
+        CUDA_TRY(cudaMemcpyAsync(c->d_avgvar, stage, sizeof(float) * (size_t)K, cudaMemcpyHostToDevice, c->stream));
     }
     c->cur_K = K;
     c->memcpy_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -554,7 +575,7 @@ static int run_mstep_accumulate(gmm_ctx* c, int K) {
 // Sum the packed statistics over all ranks (replaces the four MPI_Allreduce of
 // gaussian.cu:516,566,605,658,741 and the OpenMP-master sums) and bring them
 // to the host.
-static int reduce_stats_to_host(gmm_ctx* c, int K) {
+static int reduce_stats_device(gmm_ctx* c, int K) {
     const size_t len = (size_t)K * c->F + 1;
     timer_begin(c, c->t_reduce);
     if (c->nranks > 1) {
@@ -568,6 +589,11 @@ static int reduce_stats_to_host(gmm_ctx* c, int K) {
         }
     }
     timer_end(c, c->t_reduce);
+    return GMM_OK;
+}
+static int reduce_stats_to_host(gmm_ctx* c, int K) {
+    const size_t len = (size_t)K * c->F + 1;
+    if (int rc = reduce_stats_device(c, K)) return rc;
     CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(double) * len, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaEventRecord(c->ev_stats, c->stream));
     CUDA_TRY(cudaEventSynchronize(c->ev_stats));
@@ -705,6 +731,17 @@ int gmm_create(gmm_ctx** out, int device, int n_local, int D, int Kmax, const fl
         if (rc) { gmm_destroy(c); return rc; }
         tc_set_host_threads(c->tc, c->host_threads);
     }
+    if (const char* fm = getenv("GMM_FINALIZE")) c->finalize_mode = (std::string(fm) == "host") ? 0 : 1;
+    if (n_local > 0 && tc_estep_supported(D, Kmax)) {
+        const size_t setf = tc_param_set_floats(Kmax, D);
+        for (int b = 0; b < 2; b++) CREATE_TRY(cudaMalloc(&c->d_pset[b], sizeof(float) * setf));
+        CREATE_TRY(cudaMallocHost(&c->h_pset, sizeof(float) * setf));
+        CREATE_TRY(cudaMalloc(&c->d_avgvar, sizeof(float) * (size_t)Kmax));
+        CREATE_TRY(cudaMemsetAsync(c->d_avgvar, 0, sizeof(float) * (size_t)Kmax, c->stream));
+        CREATE_TRY(cudaMalloc(&c->d_bad, 2 * sizeof(int)));
+        CREATE_TRY(cudaMalloc(&c->d_llprev, 2 * sizeof(double)));
+        CREATE_TRY(cudaMallocHost(&c->h_small, 32 + sizeof(float) * (size_t)Kmax));
+    }
     CREATE_TRY(cudaStreamSynchronize(c->stream));
 #undef CREATE_TRY
     *out = c;
@@ -800,6 +837,9 @@ void gmm_destroy(gmm_ctx* c) {
     delete c->pool;
     cudaFree(c->d_x_aos); cudaFree(c->d_x_soa); cudaFree(c->d_memb); cudaFree(c->d_memb_saved);
     cudaFree(c->d_epack); cudaFree(c->d_stats); cudaFree(c->d_shift);
+    cudaFree(c->d_pset[0]); cudaFree(c->d_pset[1]); cudaFree(c->d_avgvar); cudaFree(c->d_bad); cudaFree(c->d_llprev);
+    if (c->h_pset) cudaFreeHost(c->h_pset);
+    if (c->h_small) cudaFreeHost(c->h_small);
     if (c->h_epack) cudaFreeHost(c->h_epack);
     if (c->h_stats) cudaFreeHost(c->h_stats);
     if (c->ev_stats) cudaEventDestroy(c->ev_stats);
@@ -822,6 +862,7 @@ static int peer_exchange_setup(gmm_ctx* c) {
     me.pid = (long long)getpid();
     me.device = c->device;
     me.ok = (G <= kXMaxRanks && getenv("GMM_NO_PEER_ALLREDUCE") == nullptr) ? 1 : 0;
+    me.dev_fin = c->d_pset[0] ? 1 : 0;
     if (me.ok && cudaMalloc(&x.base, bytes) != cudaSuccess) { x.base = nullptr; me.ok = 0; cudaGetLastError(); }
     if (me.ok) {
         cudaMemset(x.base, 0, bytes);
@@ -842,6 +883,8 @@ static int peer_exchange_setup(gmm_ctx* c) {
     cudaFree(d_all);
     int ok = 1;
     for (int p = 0; p < G; p++) ok &= all[p].ok;
+    c->dev_fin_agreed = true;
+    for (int p = 0; p < G; p++) c->dev_fin_agreed = c->dev_fin_agreed && all[p].dev_fin != 0;
     x.tab.nranks = G; x.tab.rank = c->rank; x.tab.cap = cap;
     for (int p = 0; p < G && ok; p++) {
         void* mapped = nullptr;
@@ -944,6 +987,8 @@ int gmm_set_option(gmm_ctx* c, const char* key, double value) {
     }
     else if (k == "profile") c->profile_phases = value != 0;
     else if (k == "allreduce") c->allreduce_mode = value != 0 ? 1 : 0;
+    else if (k == "finalize") { c->finalize_mode = value != 0 ? 1 : 0; if (value != 0) c->dev_fin_failed = false; }
+    else if (k == "finalize_fault_iter") c->fin_fault_iter = (int)value;
     else return fail(GMM_ERR_ARG, "gmm_set_option: unknown key '" + k + "'");
     return GMM_OK;
 }
@@ -1073,6 +1118,86 @@ static int em_iteration(gmm_ctx* c, int K, float* prev_loglik) {
     return GMM_OK;
 }
 
+// ---- EM iterations with the finalisation on the device --------------------------------------------------------
+static bool dev_finalize_ok(const gmm_ctx* c, int K) {
+    return c->finalize_mode == 1 && !c->dev_fin_failed && c->dev_fin_agreed && c->d_pset[0] && c->n > 0 && c->estep_tensor_ready && K == c->cur_K &&
+           use_tensor_estep(c, K) && tc_finalize_supported(c->tc, K);
+}
+
+// Parameter set `which` (K-prefixes of its arrays) -> pinned staging; valid after the next stream synchronisation.
+static int fetch_param_set(gmm_ctx* c, int K, int which) {
+    const int D = c->D, Kmax = c->Kmax;
+    const size_t cnt[6] = {(size_t)K, (size_t)K, (size_t)K, (size_t)K * D, (size_t)K * D * D, (size_t)K * D * D};
+    for (int a = 0; a < 6; a++) {
+        const size_t off = tc_param_set_off(Kmax, D, a);
+        CUDA_TRY(cudaMemcpyAsync(c->h_pset + off, c->d_pset[which] + off, sizeof(float) * cnt[a], cudaMemcpyDeviceToHost, c->stream));
+    }
+    return GMM_OK;
+}
+static void scatter_param_set(gmm_ctx* c, int K) {
+    const int D = c->D, Kmax = c->Kmax;
+    float* dst[6] = {c->host.N, c->host.pi, c->host.constant, c->host.means, c->host.R, c->host.Rinv};
+    const size_t cnt[6] = {(size_t)K, (size_t)K, (size_t)K, (size_t)K * D, (size_t)K * D * D, (size_t)K * D * D};
+    for (int a = 0; a < 6; a++) std::memcpy(dst[a], c->h_pset + tc_param_set_off(Kmax, D, a), sizeof(float) * cnt[a]);
+}
+
+static int em_iteration(gmm_ctx* c, int K, float* prev_loglik);
+
+// `iters` EM iterations queued back to back: M-step -> all-reduce -> finalize_params_kernel -> E-step, nothing returns to
+// the host in between.  Afterwards the host copy of the parameters is refreshed from the last set.  *ll_prev receives the
+// log-likelihood slot the LAST finalisation saw (the E-step before the last one; gmm_em's convergence test needs it).
+// If a finalisation met a cluster only the host path serves (not positive definite, outside FP16), the work queued after
+// it was discarded by the kernels themselves: the host takes the last good set, re-creates the responsibilities that
+// iteration started from and runs the remaining iterations through its own path; the context then stays on the host path.
+static int run_dev_iterations(gmm_ctx* c, int K, int iters, float* ll_prev) {
+    if (iters <= 0) return GMM_OK;
+    int* h_bad = reinterpret_cast<int*>(c->h_small);
+    double* h_ll = reinterpret_cast<double*>(c->h_small + 16);
+    h_bad[0] = -1; h_bad[1] = 0;
+    CUDA_TRY(cudaMemcpyAsync(c->d_bad, h_bad, 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    for (int i = 0; i < iters; i++) {
+        if (int rc = run_mstep_accumulate(c, K)) return rc;
+        if (int rc = reduce_stats_device(c, K)) return rc;
+        timer_begin(c, c->t_final);
+        int rc = tc_launch_finalize(c->tc, K, c->d_stats, c->d_avgvar, c->d_pset[i & 1], c->d_llprev + (i & 1), c->d_bad, i, c->fin_fault_iter, c->stream);
+        timer_end(c, c->t_final);
+        if (rc) return rc;
+        c->dev_finalize_launches++;
+        if (int rc2 = zero_stats(c, K)) return rc2;
+        if (int rc2 = run_estep(c, K)) return rc2;
+        c->iterations++;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h_bad + 2, c->d_bad, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(h_ll, c->d_llprev, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (int rc = fetch_param_set(c, K, (iters - 1) & 1)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const int first_bad = h_bad[2], code = h_bad[3];
+    if (first_bad < 0) {
+        scatter_param_set(c, K);
+        if (ll_prev) *ll_prev = (float)h_ll[(iters - 1) & 1];
+        return GMM_OK;
+    }
+    if (code == 4) return fail(GMM_ERR_NCCL, "statistics all-reduce failed (a rank did not arrive, or a cluster's statistics are not finite)");
+    c->dev_fin_failed = true;
+    c->dev_replays++;
+    if (c->verbose && c->rank == 0)
+        std::printf("[gmm] device-side finalisation met a cluster for the host path at iteration %d (code %d): replaying on the host\n", first_bad, code);
+    if (first_bad > 0) {                                   // (first_bad == 0: the host copy is still the state before the batch)
+        if (int rc = fetch_param_set(c, K, (first_bad - 1) & 1)) return rc;
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        scatter_param_set(c, K);
+    }
+    c->iterations -= iters - first_bad;
+    if (int rc = upload_params(c, K)) return rc;
+    if (int rc = zero_stats(c, K)) return rc;
+    if (int rc = run_estep(c, K)) return rc;
+    float prev = 0.f;
+    for (int i = first_bad; i < iters; i++)
+        if (int rc = em_iteration(c, K, &prev)) return rc;
+    if (ll_prev) *ll_prev = prev;
+    return GMM_OK;
+}
+
 // Bring only the log-likelihood slot of the last E-step to the host (summed over ranks).
 static int reduce_loglik_to_host(gmm_ctx* c, int K, float* out) {
     const size_t ll = (size_t)K * c->F;
@@ -1091,8 +1216,12 @@ int gmm_em_iterations(gmm_ctx* c, int K, int iters, float* loglik_out) {
     if (!c->memb_valid || K != c->cur_K) return fail(GMM_ERR_STATE, "gmm_em_iterations: run gmm_estep first");
     CUDA_TRY(cudaSetDevice(c->device));
     if (int rc = ensure_moments(c)) return rc;
-    for (int i = 0; i < iters; i++)
-        if (int rc = em_iteration(c, K, nullptr)) return rc;
+    if (dev_finalize_ok(c, K)) {
+        if (int rc = run_dev_iterations(c, K, iters, nullptr)) return rc;
+    } else {
+        for (int i = 0; i < iters; i++)
+            if (int rc = em_iteration(c, K, nullptr)) return rc;
+    }
     if (int rc = reduce_loglik_to_host(c, K, loglik_out)) return rc;
     collect_all(c);
     return GMM_OK;
@@ -1115,6 +1244,12 @@ int gmm_em(gmm_ctx* c, int K, int min_iters, int max_iters, float epsilon, float
     if (int rc = run_estep(c, K)) return rc;                 // initial E-step, gaussian.cu:487-523
     float likelihood = 0, old_likelihood = 0, change = epsilon * 2;
     int iters = 0;
+    if (min_iters > 0 && dev_finalize_ok(c, K)) {
+        // the first min_iters iterations run whatever the likelihood does (gaussian.cu:532): no convergence test, so no
+        // reason to come back to the host between them
+        if (int rc = run_dev_iterations(c, K, min_iters, &old_likelihood)) return rc;
+        iters = min_iters;
+    }
     for (;;) {
         const bool must_continue = iters < min_iters;
         const bool may_continue = iters < max_iters;
@@ -1146,11 +1281,11 @@ int gmm_get_profile(gmm_ctx* c, double out[8], int reset) {
     cudaStreamSynchronize(c->stream);
     collect_all(c);
     out[0] = c->t_estep.total_ms; out[1] = c->t_mstep.total_ms; out[2] = c->host_const_ms;
-    out[3] = c->t_reduce.total_ms; out[4] = c->memcpy_ms; out[5] = (double)c->mstep_tensor;
+    out[3] = c->t_reduce.total_ms; out[4] = c->memcpy_ms + c->t_final.total_ms; out[5] = (double)c->mstep_tensor;
     out[6] = (double)c->iterations; out[7] = (double)c->mstep_simt;
     if (reset) {
         c->t_estep.total_ms = c->t_mstep.total_ms = c->t_reduce.total_ms = c->t_fused.total_ms = 0;
-        c->host_const_ms = c->memcpy_ms = 0; c->iterations = 0;
+        c->host_const_ms = c->memcpy_ms = 0; c->iterations = 0; c->t_final.total_ms = 0;
         c->mstep_tensor = c->mstep_simt = 0;
         c->fit_reduce_ms = c->fit_seed_ms = c->fit_save_ms = 0;
     }
@@ -1180,7 +1315,8 @@ int gmm_host_pool_selftest(int threads, int jobs, int n) {
 
 int gmm_get_fit_profile(gmm_ctx* c, double out[4]) {
     if (!c || !out) return fail(GMM_ERR_ARG, "gmm_get_fit_profile: bad argument");
-    out[0] = c->fit_reduce_ms; out[1] = c->fit_seed_ms; out[2] = c->fit_save_ms; out[3] = 0;
+    out[0] = c->fit_reduce_ms; out[1] = c->fit_seed_ms; out[2] = c->fit_save_ms;
+    out[3] = (double)c->dev_finalize_launches + 1e-3 * (double)(c->dev_replays > 999 ? 999 : c->dev_replays);
     return GMM_OK;
 }
 

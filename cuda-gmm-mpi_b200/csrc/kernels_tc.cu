@@ -1265,6 +1265,244 @@ int tc_upload_params(TcState* t, const clusters_t* host, int K, cudaStream_t str
     return tc_params_commit(t, K, bad, stream);
 }
 
+// ===========================================================================
+// Device-side M-step finalisation (one CTA per cluster): everything the host does between the reduced statistics
+// and the next E-step — N, means, R (gaussian.cu:611-622, 663-679 with the rules of mstep_covariance1,
+// gaussian_kernel.cu:658-675), inverse + constant + pi (constants_kernel, :172-259) and the E-step's resident
+// operand (bimg_cluster above) — so that an EM iteration needs no device -> host -> device round trip
+// (D2H of the statistics, thread-team wake-up, H2D of the operand: 60 us of an iteration that is 3.1 ms on one GPU
+// and 0.6 ms on eight).  Same arithmetic as host_math.cpp (double, results stored as float): reverse Cholesky
+// R = U U^T, W = U^-1, Rinv = W^T W, ln det R = 2 sum ln U_ii, here with a right-looking factorisation (rank-1
+// updates of the trailing block, all threads) — the summation order differs from the host's dot products in the
+// last bit of a double.  A cluster the host would NOT serve this way (R not positive definite, factor outside FP16)
+// is not handled here: the kernel records the iteration in bad[0] (first failure wins), every later launch returns
+// immediately, and the host replays from the last good parameter set through its own path (gmm_api.cu).
+// Parameter set layout (floats, stride Kmax): N | pi | constant | means [Kmax][D] | R [Kmax][D][D] | Rinv [Kmax][D][D].
+// ===========================================================================
+__host__ __device__ inline size_t pset_off_means(int Kmax) { return 3 * (size_t)Kmax; }
+__host__ __device__ inline size_t pset_off_R(int Kmax, int D) { return pset_off_means(Kmax) + (size_t)Kmax * D; }
+__host__ __device__ inline size_t pset_off_Rinv(int Kmax, int D) { return pset_off_R(Kmax, D) + (size_t)Kmax * D * D; }
+
+template <int D>
+__global__ void __launch_bounds__(256)
+finalize_params_kernel(const double* __restrict__ stats, const float* __restrict__ avgvar, const float* __restrict__ shift_f,
+                       const double* __restrict__ scale, float* __restrict__ set, int Kmax, int K, int kp,
+                       uint8_t* __restrict__ bimg, float* __restrict__ ck, double* __restrict__ ll_out, int* __restrict__ bad, int iter,
+                       int fault_iter) {
+    using C = ECfg<D>;
+    constexpr int F = 1 + D + D * (D + 1) / 2;
+    constexpr int LD = D + 1;
+    const int k = blockIdx.x, tid = threadIdx.x;
+    if (bad[0] >= 0) return;                                   // an earlier iteration failed: leave the last good state alone
+    float* ckp = ck + (size_t)(k / 64) * 128 + (k % 64);
+    const int sg = k / C::GB, ci = k % C::GB;
+    auto rowp = [&](int d, int chunk) -> uint8_t* {            // 16-byte K chunk `chunk` of output column d (see bimg_cluster)
+        return bimg + ((size_t)sg * C::CP + d / 8) * C::B_BLOCK + (size_t)chunk * C::N * 16 + (size_t)(ci * 8 + d % 8) * 16;
+    };
+    if (k >= K) {                                              // padding: never wins the log-sum-exp, all-zero operand rows
+        if (tid == 0) { ckp[0] = -1e30f; ckp[64] = 0.f; }
+        if (k < kp)
+            for (int idx = tid; idx < D * C::NCHKB; idx += 256) *reinterpret_cast<uint4*>(rowp(idx / C::NCHKB, idx % C::NCHKB)) = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    __shared__ double sA[D][LD], sW[D][LD], sdiag[D], sm[D], svd[D], sredd[8];
+    __shared__ float swr[D][LD], smu[D], sredf[8];
+    __shared__ int sbad;
+    const double* s = stats + (size_t)k * F;
+    const double S0 = s[0];
+    const float Nf = (float)S0;
+    // ---- pi: N[k] over the sum of all N (compute_pi, gaussian_kernel.cu:172-193) ----
+    double part = 0.0;
+    for (int kk = tid; kk < K; kk += 256) part += (double)(float)stats[(size_t)kk * F];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((tid & 31) == 0) sredd[tid >> 5] = part;
+    if (tid == 0) sbad = 0;
+    __syncthreads();
+    double sumN = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) sumN += sredd[w];
+    const float pik = Nf < 0.5f ? 1e-10f : (float)((double)Nf / sumN);
+    if (k == 0 && tid == 0) {
+        *ll_out = stats[(size_t)K * F];                        // log-likelihood of the E-step these statistics came from
+        if (isnan(S0)) atomicMax(&sbad, 4);                    // the all-reduce kernel marks a failed exchange with NaN
+        if (iter == fault_iter) atomicMax(&sbad, 1);           // test hook (option "finalize_fault_iter"): exercise the host replay
+    }
+    // ---- means (gaussian.cu:611-622) ----
+    if (tid < D) {
+        const double m = (S0 != 0.0) ? s[1 + tid] / S0 : 0.0;
+        sm[tid] = m;
+        const float mu = (Nf > 0.5f) ? (float)(m + (double)shift_f[tid]) : 0.0f;
+        smu[tid] = mu;
+        set[pset_off_means(Kmax) + (size_t)k * D + tid] = mu;
+    }
+    __syncthreads();
+    // ---- R (gaussian.cu:663-679, gaussian_kernel.cu:658-675) ----
+    {
+        float* R = set + pset_off_R(Kmax, D) + (size_t)k * D * D;
+        const double inv = 1.0 / (double)Nf;
+        const float av = avgvar[k];
+        for (int idx = tid; idx < D * D; idx += 256) {
+            const int i = idx / D, j = idx % D;
+            if (j > i) continue;
+            float v;
+            if (Nf > 0.5f) {
+                double cov = (Nf >= 1.0f) ? s[1 + D + i * (i + 1) / 2 + j] - sm[i] * s[1 + j] : 0.0;
+                if (i == j) cov += av;
+                v = (float)(cov * inv);
+            } else {
+                v = (i == j) ? 1.0f : 0.0f;
+            }
+            R[i * D + j] = v; R[j * D + i] = v;
+            sA[i][j] = (double)v; sA[j][i] = (double)v;
+        }
+    }
+    __syncthreads();
+    // ---- R = U U^T, right-looking from the last column; U ends up in the upper triangle of sA, its diagonal in sdiag ----
+    bool ok = true;
+    for (int j = D - 1; j >= 0; j--) {
+        const double d = sA[j][j];
+        if (!(d > 0.0) || !isfinite(d)) { ok = false; break; }    // the same value in every thread
+        const double rp = rsqrt(d);                               // sdiag holds 1 / U_jj: only reciprocals are needed below
+        if (tid < j) sA[tid][j] *= rp;
+        if (tid == 0) { sdiag[j] = rp; sm[j] = d; }               // (the means in sm are not needed any more)
+        __syncthreads();
+        for (int idx = tid; idx < j * j; idx += 256) {
+            const int i = idx / j, m = idx - i * j;
+            sA[i][m] -= sA[i][j] * sA[m][j];
+        }
+        __syncthreads();
+    }
+    if (!ok) {
+        if (tid == 0) { atomicCAS(&bad[0], -1, iter); atomicMax(&bad[1], 1); }
+        return;
+    }
+    // ---- W = U^-1 (upper triangular), one column per thread ----
+    if (tid < D) {
+        const int j = tid;
+        for (int i = D - 1; i > j; i--) sW[i][j] = 0.0;
+        sW[j][j] = sdiag[j];
+        for (int i = j - 1; i >= 0; i--) {
+            double v = 0.0;
+            for (int m = i + 1; m <= j; m++) v -= sA[i][m] * sW[m][j];
+            sW[i][j] = v * sdiag[i];
+        }
+    }
+    // ln det R = sum ln U_jj^2 = sum ln d_j (d_j = the pivots before the square root), one logarithm per thread
+    double ld2 = (tid >= 32 && tid < 32 + D) ? log(sm[tid - 32]) : 0.0;
+    if (tid >= 32 && tid < 64) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ld2 += __shfl_xor_sync(0xffffffffu, ld2, o);
+        if (tid == 32) sredd[0] = ld2;
+    }
+    __syncthreads();
+    const double ld = 0.5 * sredd[0];                          // sum ln U_jj
+    // ---- Rinv = W^T W, constant (gaussian_kernel.cu:241), N, pi ----
+    {
+        float* Ri = set + pset_off_Rinv(Kmax, D) + (size_t)k * D * D;
+        for (int idx = tid; idx < D * D; idx += 256) {
+            const int i = idx / D, j = idx % D;
+            if (j < i) continue;
+            double v = 0.0;
+            for (int m = 0; m <= i; m++) v += sW[m][i] * sW[m][j];
+            Ri[i * D + j] = (float)v; Ri[j * D + i] = (float)v;
+        }
+    }
+    const float cst = (float)(-D * 0.5 * log(2.0 * 3.1415926535897931) - 0.5 * (2.0 * ld));
+    if (tid == 0) { set[k] = Nf; set[Kmax + k] = pik; set[2 * (size_t)Kmax + k] = cst; }
+    // ---- E-step operand rows:  y_d = sum_j W'[d][j] z_j + v_d,  W'[d][j] = W[d][j] * scale_j (j >= d),  v = -W (mu - shift) ----
+    float amax = 0.f;
+    if (tid < D) {
+        double v = 0.0;
+        for (int j = tid; j < D; j++) v -= sW[tid][j] * ((double)smu[j] - (double)shift_f[j]);
+        svd[tid] = v;
+        amax = fabsf((float)fabs(v));
+    }
+    for (int idx = tid; idx < D * D; idx += 256) {
+        const int d = idx / D, j = idx % D;
+        const float w = (j >= d) ? (float)(sW[d][j] * scale[j]) : 0.f;
+        swr[d][j] = w;
+        amax = fmaxf(amax, fabsf(w));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((tid & 31) == 0) sredf[tid >> 5] = amax;
+    __syncthreads();
+    amax = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) amax = fmaxf(amax, sredf[w]);
+    if (!isfinite(amax)) {
+        if (tid == 0) { atomicCAS(&bad[0], -1, iter); atomicMax(&bad[1], 2); }
+        return;
+    }
+    // per-cluster power-of-two scale: the largest operand entry lands in [2^12, 2^13) (see bimg_cluster)
+    int e2 = amax > 0.f ? 12 - ilogbf(amax) : 0;
+    e2 = e2 > 40 ? 40 : (e2 < -40 ? -40 : e2);
+    for (int idx = tid; idx < D * C::CP; idx += 256) {
+        const int d = idx / C::CP, c = idx % C::CP;
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const float w0 = ldexpf(swr[d][8 * c + 2 * e], e2), w1 = ldexpf(swr[d][8 * c + 2 * e + 1], e2);
+            const __half2 h = __floats2half2_rn(w0, w1);
+            const float2 hf = __half22float2(h);
+            hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[e] = pack_half2(w0 - hf.x, w1 - hf.y);          // exact difference: hi is w rounded to 11 bits
+        }
+        *reinterpret_cast<uint4*>(rowp(d, c)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);             // x (zh_c, zl_c) [aliased]
+        *reinterpret_cast<uint4*>(rowp(d, C::CP + c)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);     // x zh_c
+    }
+    if (tid < D) {
+        const double vs = ldexp(svd[tid], e2);
+        const float vf = (float)vs;
+        if (!(fabsf(vf) < 6.0e4f)) atomicMax(&sbad, 2);
+        const __half vh = __float2half_rn(vf);
+        const __half vl = __float2half_rn((float)(vs - (double)__half2float(vh)));
+        const uint32_t p = (uint32_t)__half_as_ushort(vh) | ((uint32_t)__half_as_ushort(vl) << 16);
+        *reinterpret_cast<uint4*>(rowp(tid, 2 * C::CP)) = make_uint4(p, 0u, 0u, 0u);
+        if (C::NCHKB > 2 * C::CP + 1) *reinterpret_cast<uint4*>(rowp(tid, 2 * C::CP + 1)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (tid == 0) {
+        ckp[0] = cst + logf(pik);                              // additive term of estep1 (gaussian_kernel.cu:442)
+        ckp[64] = (float)ldexp(-0.5 * 1.4426950408889634, -2 * e2);
+    }
+    __syncthreads();
+    if (tid == 0 && sbad) { atomicCAS(&bad[0], -1, iter); atomicMax(&bad[1], sbad); }
+}
+
+size_t tc_param_set_floats(int Kmax, int D) { return (size_t)Kmax * (3 + (size_t)D + 2 * (size_t)D * D); }
+size_t tc_param_set_off(int Kmax, int D, int which) {
+    switch (which) {
+        case 0: return 0;                                   // N
+        case 1: return (size_t)Kmax;                        // pi
+        case 2: return 2 * (size_t)Kmax;                    // constant
+        case 3: return pset_off_means(Kmax);
+        case 4: return pset_off_R(Kmax, D);
+        default: return pset_off_Rinv(Kmax, D);
+    }
+}
+bool tc_finalize_supported(const TcState* t, int K) {
+    return t && t->emap_ok && t->have_shift && tc_estep_supported(t->D, K) && tc_estep_range_ok(t);
+}
+int tc_launch_finalize(TcState* t, int K, const double* d_stats, const float* d_avgvar, float* d_set, double* d_ll, int* d_bad, int iter,
+                       int fault_iter, cudaStream_t stream) {
+    if (!tc_finalize_supported(t, K)) return fail(GMM_ERR_STATE, "device-side finalisation not available for this state");
+    const int kp = tc_params_padded(t, K);
+    const int grid = ((K + 63) / 64) * 64;                     // whole passes: the padding clusters of the last pass get their constants
+#define GMM_FIN(d) finalize_params_kernel<d><<<grid, 256, 0, stream>>>(d_stats, d_avgvar, t->d_shift_f, t->d_scale, d_set, t->Kmax, K, kp, \
+                                                                     t->d_bimg, t->d_ck, d_ll, d_bad, iter, fault_iter)
+    switch (t->D) {
+        case 8: GMM_FIN(8); break;
+        case 16: GMM_FIN(16); break;
+        case 24: GMM_FIN(24); break;
+        default: return fail(GMM_ERR_ARG, "device-side finalisation: unsupported D");
+    }
+#undef GMM_FIN
+    TC_CUDA_TRY(cudaGetLastError());
+    t->e_NG = (K + 15) / 16;
+    return GMM_OK;
+}
+
 template <int D>
 static int launch_estep_d(TcState* t, int K, double* d_ll, cudaStream_t stream) {
     using C = ECfg<D>;

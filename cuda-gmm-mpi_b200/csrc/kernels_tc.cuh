@@ -38,6 +38,17 @@ int  tc_params_cluster(TcState*, const clusters_t* host, int k, int K);
 int  tc_params_cluster_w(TcState*, const clusters_t* host, int k, int K, const double* W);
 int  tc_params_commit(TcState*, int K, int bad, cudaStream_t stream);
 int  tc_launch_estep(TcState*, int K, double* d_ll, cudaStream_t stream);
+// Device-side M-step finalisation: reduced statistics -> parameter set `d_set` (floats, tc_param_set_floats(); arrays at
+// tc_param_set_off(which = 0 N, 1 pi, 2 constant, 3 means, 4 R, 5 Rinv), stride Kmax) + the E-step operand, no host round
+// trip.  d_ll[0] receives the log-likelihood slot of the statistics.  d_bad[0] = first iteration (`iter`) that met a cluster
+// the host path must handle (-1: none; later launches then return immediately), d_bad[1] = its code (1 not positive
+// definite, 2 outside FP16, 4 statistics not finite).
+bool tc_finalize_supported(const TcState*, int K);
+size_t tc_param_set_floats(int Kmax, int D);
+size_t tc_param_set_off(int Kmax, int D, int which);
+// fault_iter: the launch with iter == fault_iter reports code 1 although nothing is wrong (-1: never; test hook).
+int  tc_launch_finalize(TcState*, int K, const double* d_stats, const float* d_avgvar, float* d_set, double* d_ll, int* d_bad, int iter,
+                        int fault_iter, cudaStream_t stream);
 // Accumulates sum_n g[k][n] * phi_f(x_n - shift) into d_stats[k*F + f] (double, original units).
 int  tc_launch_mstep(TcState*, int K, double* d_stats, cudaStream_t stream);
 

@@ -278,7 +278,8 @@ class Engine:
     def fit_profile(self):
         out = (C.c_double * 4)()
         _check(self.lib.gmm_get_fit_profile(self.h, out))
-        return dict(reduce_order_ms=out[0], seed_ms=out[1], save_ms=out[2])
+        return dict(reduce_order_ms=out[0], seed_ms=out[1], save_ms=out[2], device_finalize_launches=int(out[3]),
+                    host_replays=int(round((out[3] - int(out[3])) * 1000)))
 
     def comm_rank(self):
         r, n = C.c_int(), C.c_int()

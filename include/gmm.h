@@ -113,10 +113,18 @@ int  gmm_comm_rank(const gmm_ctx*, int* rank, int* nranks);
  * "allreduce" (1, default = the per-iteration sum of the packed statistics runs
  * as this library's own kernel over NVLink peer memory when every rank could map
  * every other rank's exchange area — one box, <= 8 GPUs; 0 = ncclAllReduce),
- * "mstep_gamma_split" (tensor M-step: 1 = responsibilities enter the MMA as
- * an FP16 hi/lo pair, 0 = as one round-to-nearest FP16 value (10 % faster
- * kernel, ~1.4e-4/sqrt(N_k) statistical error per cluster), 2 (default) =
- * pair whenever a cluster has fewer than 2048 events).  Unknown keys are an
+ * "finalize" (1, default = when the tensor E-step serves the parameters, the
+ * whole step between the reduced statistics and the next E-step — N, means, R,
+ * inverse, constants, pi and the E-step operand — runs as ONE kernel on the
+ * device and gmm_em_iterations / the first min_iters iterations of gmm_em queue
+ * their iterations back to back without returning to the host; a cluster that
+ * needs the host's no-pivot LU semantics (R not positive definite) or leaves the
+ * FP16 operand range makes the library replay from the last good parameters
+ * through the host path and stay on it; 0 = host finalisation every iteration,
+ * invert_matrix.cpp semantics; env GMM_FINALIZE=host|device sets the default),
+ * "finalize_fault_iter" (tests: that iteration of the next batch reports a
+ * failure although nothing is wrong, -1 = never).  Options have to be set
+ * identically on every rank of a communicator.  Unknown keys are an
  * error (GMM_ERR_ARG).  Every E-step materialises the memberships on the
  * device (the reference's behaviour); they reach the host only through
  * gmm_get_clusters / gmm_fit.                                              */
@@ -148,7 +156,8 @@ int  gmm_mstep(gmm_ctx*, int K);
 
 /* constants_kernel semantics: Rinv, constant (ln det), pi
  * (gaussian_kernel.cu:107-259, gaussian.cu:698-708).  The DxD inversion runs
- * on the host (north_star: invert_matrix.cpp semantics).                    */
+ * on the host here (invert_matrix.cpp semantics); inside gmm_em /
+ * gmm_em_iterations see option "finalize".                                  */
 int  gmm_constants(gmm_ctx*, int K);
 
 /* The EM loop of gaussian.cu:532-755 (preceded by the initial E-step of
@@ -167,14 +176,16 @@ int  gmm_em_iterations(gmm_ctx*, int K, int iters, float* loglik_out);
 /* Per-phase device/host time accumulated since the last reset, in ms
  * (replaces profile_t, gaussian.cu:76-106,967).
  * out[0]=estep out[1]=mstep out[2]=constants(host) out[3]=allreduce
- * out[4]=parameter finalisation + upload (host) out[6]=iterations
- * out[5] / out[7] = tensor M-step launches with the responsibilities as an
- * FP16 hi/lo pair (three MMA products) / as one FP16 value (two products)   */
+ * out[4]=parameter finalisation + operand upload (host time, or the device
+ * kernel's time with option "finalize") out[6]=iterations
+ * out[5] / out[7] = M-step launches of the tensor / the SIMT kernel         */
 int  gmm_get_profile(gmm_ctx*, double out[8], int reset);
 
 /* Host-side phases of gmm_fit since the last gmm_get_profile(reset=1), in ms:
  * out[0]=order reduction (gaussian.cu:860-907: empties, pair search, merge)
- * out[1]=seeding (:390-452) out[2]=saving the best configuration (:839-851) */
+ * out[1]=seeding (:390-452) out[2]=saving the best configuration (:839-851)
+ * out[3]=launches of the device-side finalisation since the context was
+ * created + 0.001 x the number of host replays (see option "finalize")     */
 int  gmm_get_fit_profile(gmm_ctx*, double out[4]);
 
 /* Model-order reduction driver (gaussian.cu:479-960): for K = K0 .. stop:

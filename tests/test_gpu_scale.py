@@ -237,3 +237,65 @@ def test_upload_events_file_equals_array(loaded, tmp_path):
     with pkg.Engine(None, K, n_global=N + 1, offset=0, n_local=n, D=D) as eng:
         with pytest.raises(pkg.GmmError):
             eng.upload_events_file(path)
+
+
+def _run_iterations(pkg, ev, K, n, finalize, fault=None, em=False):
+    with pkg.Engine(ev, K) as eng:
+        eng.set_option("finalize", finalize)
+        if fault is not None:
+            eng.set_option("finalize_fault_iter", fault)
+        eng.seed(K)
+        if em:
+            ll, iters = eng.em(K, n, n)
+            assert iters == n
+        else:
+            eng.estep(K)
+            ll = eng.em_iterations(K, n)
+        got = eng.get_clusters(K, with_memberships=True)
+        fp = eng.fit_profile()
+        # a second batch in the same context (after a replay the context stays on the host path)
+        ll2 = eng.em_iterations(K, 2)
+        got2 = eng.get_clusters(K, with_memberships=True)
+        fp2 = eng.fit_profile()
+    return got, ll, fp, got2, ll2, fp2
+
+
+@pytest.mark.parametrize("shape", [(30_000, 8, 6), (20_000, 16, 20), (25_000, 24, 64), (9_000, 24, 100)])
+def test_device_finalisation_equals_host_finalisation(loaded, shape):
+    """Option "finalize": the one-kernel device-side step between the reduced statistics and the next E-step (N, means, R,
+    inverse, constants, pi, E-step operand) against the host finalisation of the same library — same arithmetic, so the
+    two runs agree far inside the run-level tolerance — through gmm_em_iterations and through gmm_em (K > 64 included:
+    two operand passes)."""
+    pkg = loaded
+    N, D, K = shape
+    n = 6
+    ev = pkg.synth.make_blobs(N, D, K, seed=77)
+    for em in (False, True):
+        host, ll_h, fp_h, host2, ll2_h, _ = _run_iterations(pkg, ev, K, n, 0, em=em)
+        dev, ll_d, fp_d, dev2, ll2_d, fp2_d = _run_iterations(pkg, ev, K, n, 1, em=em)
+        assert fp_h["device_finalize_launches"] == 0
+        assert fp_d["device_finalize_launches"] == n and fp_d["host_replays"] == 0
+        assert fp2_d["device_finalize_launches"] == n + 2
+        for a, b, la, lb in ((dev, host, ll_d, ll_h), (dev2, host2, ll2_d, ll2_h)):
+            assert abs(la - lb) <= 2e-6 * abs(lb)
+            assert_params_close(a, b, K, rtol_N=2e-5)
+            np.testing.assert_allclose(a.memberships, b.memberships, rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("fault", [0, 3, 5])
+def test_device_finalisation_replay_on_the_host(loaded, fault):
+    """A finalisation that reports a cluster for the host path (forced by the test hook at iteration `fault` of 6): the
+    work queued after it is discarded, the library replays from the last good parameter set through the host path, the
+    result equals the all-host run, and the context stays on the host path afterwards."""
+    pkg = loaded
+    N, D, K, n = 25_000, 24, 32, 6
+    ev = pkg.synth.make_blobs(N, D, K, seed=78)
+    for em in (False, True):
+        host, ll_h, _, host2, ll2_h, _ = _run_iterations(pkg, ev, K, n, 0, em=em)
+        rep, ll_r, fp, rep2, ll2_r, fp2 = _run_iterations(pkg, ev, K, n, 1, fault=fault, em=em)
+        assert fp["host_replays"] == 1 and fp["device_finalize_launches"] == n
+        assert fp2["device_finalize_launches"] == n and fp2["host_replays"] == 1     # second batch: host path
+        for a, b, la, lb in ((rep, host, ll_r, ll_h), (rep2, host2, ll2_r, ll2_h)):
+            assert abs(la - lb) <= 2e-6 * abs(lb)
+            assert_params_close(a, b, K, rtol_N=2e-5)
+            np.testing.assert_allclose(a.memberships, b.memberships, rtol=0, atol=2e-5)
