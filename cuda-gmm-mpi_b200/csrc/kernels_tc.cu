@@ -1289,6 +1289,11 @@ finalize_params_kernel(const double* __restrict__ stats, const float* __restrict
                        const double* __restrict__ scale, float* __restrict__ set, int Kmax, int K, int kp,
                        uint8_t* __restrict__ bimg, float* __restrict__ ck, double* __restrict__ ll_out, int* __restrict__ bad, int iter,
                        int fault_iter) {
+    // Latency-bound by construction (one CTA works through a 24 x 24 factorisation, 64 CTAs on 148 SMs): one global round trip
+    // (the cluster's statistics row is staged in shared memory), one barrier per column of the factorisation and per row of the
+    // triangular inverse (rank-1 updates by all threads instead of per-thread dot products).  Measured 24 us per launch at
+    // K = 64, D = 24 (ncu: 51 k cycles, issue slots 13 % used, half of the warp samples waiting at a barrier) — the same as a first
+    // version with per-thread dot products and two barriers per column, so the remaining time is not in those chains.
     using C = ECfg<D>;
     constexpr int F = 1 + D + D * (D + 1) / 2;
     constexpr int LD = D + 1;
@@ -1305,71 +1310,75 @@ finalize_params_kernel(const double* __restrict__ stats, const float* __restrict
             for (int idx = tid; idx < D * C::NCHKB; idx += 256) *reinterpret_cast<uint4*>(rowp(idx / C::NCHKB, idx % C::NCHKB)) = make_uint4(0u, 0u, 0u, 0u);
         return;
     }
-    __shared__ double sA[D][LD], sW[D][LD], sdiag[D], sm[D], svd[D], sredd[8];
-    __shared__ float swr[D][LD], smu[D], sredf[8];
+    __shared__ double sS[F + 3], sA[D][LD], sU[D][LD], sW[D][LD], srd[D], spiv[D], sdm[D], sscale[D], svd[D], sredd[8];
+    __shared__ float swr[D][LD], sredf[8];
     __shared__ int sbad;
+    // ---- stage: the statistics row, the S0 of every cluster (pi), shift / scale ----
     const double* s = stats + (size_t)k * F;
-    const double S0 = s[0];
-    const float Nf = (float)S0;
-    // ---- pi: N[k] over the sum of all N (compute_pi, gaussian_kernel.cu:172-193) ----
+    for (int f = tid; f < F; f += 256) sS[f] = s[f];
     double part = 0.0;
     for (int kk = tid; kk < K; kk += 256) part += (double)(float)stats[(size_t)kk * F];
+    double shift_d = 0.0;
+    if (tid < D) { shift_d = (double)shift_f[tid]; sscale[tid] = scale[tid]; }
+    const float av = avgvar[k];
+    double ll_slot = 0.0;
+    if (k == 0 && tid == 0) ll_slot = stats[(size_t)K * F];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     if ((tid & 31) == 0) sredd[tid >> 5] = part;
     if (tid == 0) sbad = 0;
     __syncthreads();
+    const double S0 = sS[0];
+    const float Nf = (float)S0;
+    if (k == 0 && tid == 0) {
+        *ll_out = ll_slot;                                     // log-likelihood of the E-step these statistics came from
+        if (isnan(S0)) atomicMax(&sbad, 4);                    // the all-reduce kernel marks a failed exchange with NaN
+        if (iter == fault_iter) atomicMax(&sbad, 1);           // test hook (option "finalize_fault_iter"): exercise the host replay
+    }
+    // ---- pi (compute_pi, gaussian_kernel.cu:172-193), means (gaussian.cu:611-622), R (:663-679, gaussian_kernel.cu:658-675) ----
     double sumN = 0.0;
 #pragma unroll
     for (int w = 0; w < 8; w++) sumN += sredd[w];
     const float pik = Nf < 0.5f ? 1e-10f : (float)((double)Nf / sumN);
-    if (k == 0 && tid == 0) {
-        *ll_out = stats[(size_t)K * F];                        // log-likelihood of the E-step these statistics came from
-        if (isnan(S0)) atomicMax(&sbad, 4);                    // the all-reduce kernel marks a failed exchange with NaN
-        if (iter == fault_iter) atomicMax(&sbad, 1);           // test hook (option "finalize_fault_iter"): exercise the host replay
-    }
-    // ---- means (gaussian.cu:611-622) ----
     if (tid < D) {
-        const double m = (S0 != 0.0) ? s[1 + tid] / S0 : 0.0;
-        sm[tid] = m;
-        const float mu = (Nf > 0.5f) ? (float)(m + (double)shift_f[tid]) : 0.0f;
-        smu[tid] = mu;
+        const double m = (S0 != 0.0) ? sS[1 + tid] / S0 : 0.0;
+        const float mu = (Nf > 0.5f) ? (float)(m + shift_d) : 0.0f;
+        sdm[tid] = (double)mu - shift_d;                       // mu - shift as the operand rows need it
         set[pset_off_means(Kmax) + (size_t)k * D + tid] = mu;
     }
-    __syncthreads();
-    // ---- R (gaussian.cu:663-679, gaussian_kernel.cu:658-675) ----
     {
         float* R = set + pset_off_R(Kmax, D) + (size_t)k * D * D;
         const double inv = 1.0 / (double)Nf;
-        const float av = avgvar[k];
         for (int idx = tid; idx < D * D; idx += 256) {
             const int i = idx / D, j = idx % D;
             if (j > i) continue;
             float v;
             if (Nf > 0.5f) {
-                double cov = (Nf >= 1.0f) ? s[1 + D + i * (i + 1) / 2 + j] - sm[i] * s[1 + j] : 0.0;
+                const double mi = (S0 != 0.0) ? sS[1 + i] / S0 : 0.0;
+                double cov = (Nf >= 1.0f) ? sS[1 + D + i * (i + 1) / 2 + j] - mi * sS[1 + j] : 0.0;
                 if (i == j) cov += av;
                 v = (float)(cov * inv);
             } else {
                 v = (i == j) ? 1.0f : 0.0f;
             }
             R[i * D + j] = v; R[j * D + i] = v;
-            sA[i][j] = (double)v; sA[j][i] = (double)v;
+            sA[j][i] = (double)v;                              // upper triangle (row <= column) is what the factorisation reads
+            if (i == j) sW[i][i] = 0.0; else { sW[j][i] = 0.0; sW[i][j] = 0.0; }
         }
     }
     __syncthreads();
-    // ---- R = U U^T, right-looking from the last column; U ends up in the upper triangle of sA, its diagonal in sdiag ----
+    // ---- R = U U^T from the last column: ONE barrier per column.  sA keeps the unscaled trailing block (upper triangle),
+    //      the scaled column goes to sU, its reciprocal pivot to srd, the pivot's square to spiv (ln det) ----
     bool ok = true;
     for (int j = D - 1; j >= 0; j--) {
         const double d = sA[j][j];
         if (!(d > 0.0) || !isfinite(d)) { ok = false; break; }    // the same value in every thread
-        const double rp = rsqrt(d);                               // sdiag holds 1 / U_jj: only reciprocals are needed below
-        if (tid < j) sA[tid][j] *= rp;
-        if (tid == 0) { sdiag[j] = rp; sm[j] = d; }               // (the means in sm are not needed any more)
-        __syncthreads();
-        for (int idx = tid; idx < j * j; idx += 256) {
-            const int i = idx / j, m = idx - i * j;
-            sA[i][m] -= sA[i][j] * sA[m][j];
+        const double rp = rsqrt(d), invd = rp * rp;
+        if (tid < j) sU[tid][j] = sA[tid][j] * rp;
+        else if (tid == j) { srd[j] = rp; spiv[j] = d; }
+        for (int idx = tid; idx < D * D; idx += 256) {            // (i, m) with i <= m < j:  A[i][m] -= A[i][j] A[m][j] / d
+            const int i = idx / D, m = idx % D;
+            if (i <= m && m < j) sA[i][m] -= sA[i][j] * sA[m][j] * invd;
         }
         __syncthreads();
     }
@@ -1377,57 +1386,61 @@ finalize_params_kernel(const double* __restrict__ stats, const float* __restrict
         if (tid == 0) { atomicCAS(&bad[0], -1, iter); atomicMax(&bad[1], 1); }
         return;
     }
-    // ---- W = U^-1 (upper triangular), one column per thread ----
-    if (tid < D) {
-        const int j = tid;
-        for (int i = D - 1; i > j; i--) sW[i][j] = 0.0;
-        sW[j][j] = sdiag[j];
-        for (int i = j - 1; i >= 0; i--) {
-            double v = 0.0;
-            for (int m = i + 1; m <= j; m++) v -= sA[i][m] * sW[m][j];
-            sW[i][j] = v * sdiag[i];
-        }
-    }
-    // ln det R = sum ln U_jj^2 = sum ln d_j (d_j = the pivots before the square root), one logarithm per thread
-    double ld2 = (tid >= 32 && tid < 32 + D) ? log(sm[tid - 32]) : 0.0;
-    if (tid >= 32 && tid < 64) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ld2 += __shfl_xor_sync(0xffffffffu, ld2, o);
-        if (tid == 32) sredd[0] = ld2;
-    }
+    // ---- W = U^-1 (upper triangular), row by row from the bottom, ONE barrier per row: when row m is final, every row i < m
+    //      takes its term U[i][m] W[m][j]; the thread that completes row m - 1 scales it (W[i][j] = -(sum) / U[i][i]) ----
+    if (tid < D) sW[tid][tid] = srd[tid];
     __syncthreads();
-    const double ld = 0.5 * sredd[0];                          // sum ln U_jj
-    // ---- Rinv = W^T W, constant (gaussian_kernel.cu:241), N, pi ----
+    for (int m = D - 1; m >= 1; m--) {
+        for (int idx = tid; idx < D * D; idx += 256) {
+            const int i = idx / D, j = idx % D;
+            if (i < m && j >= m) {
+                double acc = sW[i][j] + sU[i][m] * sW[m][j];
+                if (i == m - 1) acc = -acc * srd[i];
+                sW[i][j] = acc;
+            }
+        }
+        __syncthreads();
+    }
+    // ---- Rinv = W^T W, ln det, constant (gaussian_kernel.cu:241), N, pi; operand rows: W'[d][j] = W[d][j] * scale_j, v = -W (mu - shift) ----
     {
         float* Ri = set + pset_off_Rinv(Kmax, D) + (size_t)k * D * D;
         for (int idx = tid; idx < D * D; idx += 256) {
             const int i = idx / D, j = idx % D;
             if (j < i) continue;
             double v = 0.0;
+#pragma unroll 4
             for (int m = 0; m <= i; m++) v += sW[m][i] * sW[m][j];
             Ri[i * D + j] = (float)v; Ri[j * D + i] = (float)v;
         }
     }
-    const float cst = (float)(-D * 0.5 * log(2.0 * 3.1415926535897931) - 0.5 * (2.0 * ld));
-    if (tid == 0) { set[k] = Nf; set[Kmax + k] = pik; set[2 * (size_t)Kmax + k] = cst; }
-    // ---- E-step operand rows:  y_d = sum_j W'[d][j] z_j + v_d,  W'[d][j] = W[d][j] * scale_j (j >= d),  v = -W (mu - shift) ----
     float amax = 0.f;
-    if (tid < D) {
-        double v = 0.0;
-        for (int j = tid; j < D; j++) v -= sW[tid][j] * ((double)smu[j] - (double)shift_f[j]);
-        svd[tid] = v;
-        amax = fabsf((float)fabs(v));
-    }
     for (int idx = tid; idx < D * D; idx += 256) {
         const int d = idx / D, j = idx % D;
-        const float w = (j >= d) ? (float)(sW[d][j] * scale[j]) : 0.f;
+        const float w = (j >= d) ? (float)(sW[d][j] * sscale[j]) : 0.f;
         swr[d][j] = w;
         amax = fmaxf(amax, fabsf(w));
+    }
+    if (tid >= 64 && tid < 64 + D) {                              // (a warp of its own: the row sums are serial)
+        const int d = tid - 64;
+        double v = 0.0;
+#pragma unroll 4
+        for (int j = d; j < D; j++) v -= sW[d][j] * sdm[j];
+        svd[d] = v;
+        amax = fmaxf(amax, (float)fabs(v));
+    }
+    double ld2 = (tid >= 32 && tid < 32 + D) ? log(spiv[tid - 32]) : 0.0;   // ln det R = sum ln (pivot^2)
+    if (tid >= 32 && tid < 64) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ld2 += __shfl_xor_sync(0xffffffffu, ld2, o);
+        if (tid == 32) sredd[0] = ld2;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     if ((tid & 31) == 0) sredf[tid >> 5] = amax;
     __syncthreads();
+    const double ld = 0.5 * sredd[0];                          // sum ln U_jj
+    const float cst = (float)(-D * 0.5 * log(2.0 * 3.1415926535897931) - 0.5 * (2.0 * ld));
+    if (tid == 0) { set[k] = Nf; set[Kmax + k] = pik; set[2 * (size_t)Kmax + k] = cst; }
     amax = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; w++) amax = fmaxf(amax, sredf[w]);
@@ -1452,15 +1465,16 @@ finalize_params_kernel(const double* __restrict__ stats, const float* __restrict
         *reinterpret_cast<uint4*>(rowp(d, c)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);             // x (zh_c, zl_c) [aliased]
         *reinterpret_cast<uint4*>(rowp(d, C::CP + c)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);     // x zh_c
     }
-    if (tid < D) {
-        const double vs = ldexp(svd[tid], e2);
+    if (tid >= 128 && tid < 128 + D) {
+        const int d = tid - 128;
+        const double vs = ldexp(svd[d], e2);
         const float vf = (float)vs;
         if (!(fabsf(vf) < 6.0e4f)) atomicMax(&sbad, 2);
         const __half vh = __float2half_rn(vf);
         const __half vl = __float2half_rn((float)(vs - (double)__half2float(vh)));
         const uint32_t p = (uint32_t)__half_as_ushort(vh) | ((uint32_t)__half_as_ushort(vl) << 16);
-        *reinterpret_cast<uint4*>(rowp(tid, 2 * C::CP)) = make_uint4(p, 0u, 0u, 0u);
-        if (C::NCHKB > 2 * C::CP + 1) *reinterpret_cast<uint4*>(rowp(tid, 2 * C::CP + 1)) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(rowp(d, 2 * C::CP)) = make_uint4(p, 0u, 0u, 0u);
+        if (C::NCHKB > 2 * C::CP + 1) *reinterpret_cast<uint4*>(rowp(d, 2 * C::CP + 1)) = make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid == 0) {
         ckp[0] = cst + logf(pik);                              // additive term of estep1 (gaussian_kernel.cu:442)
