@@ -1283,18 +1283,30 @@ __host__ __device__ inline size_t pset_off_means(int Kmax) { return 3 * (size_t)
 __host__ __device__ inline size_t pset_off_R(int Kmax, int D) { return pset_off_means(Kmax) + (size_t)Kmax * D; }
 __host__ __device__ inline size_t pset_off_Rinv(int Kmax, int D) { return pset_off_R(Kmax, D) + (size_t)Kmax * D * D; }
 
+#ifdef GMM_FIN_PROF   // build-time phase stamps of finalize_params_kernel (CTA 0, thread 0 prints cycle deltas); off by default
+#define FIN_STAMP(i) do { if (k == 0 && tid == 0) fin_t[i] = clock64(); } while (0)
+#else
+#define FIN_STAMP(i) do { } while (0)
+#endif
+
+template <int D> struct FinCfg { static constexpr int T = (D * D > 256 ? (D * D + 31) / 32 * 32 : 256), NW = T / 32; };   // a thread per matrix element
+
 template <int D>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(FinCfg<D>::T)
 finalize_params_kernel(const double* __restrict__ stats, const float* __restrict__ avgvar, const float* __restrict__ shift_f,
                        const double* __restrict__ scale, float* __restrict__ set, int Kmax, int K, int kp,
                        uint8_t* __restrict__ bimg, float* __restrict__ ck, double* __restrict__ ll_out, int* __restrict__ bad, int iter,
                        int fault_iter) {
-    // Latency-bound by construction (one CTA works through a 24 x 24 factorisation, 64 CTAs on 148 SMs): one global round trip
-    // (the cluster's statistics row is staged in shared memory), one barrier per column of the factorisation and per row of the
-    // triangular inverse (rank-1 updates by all threads instead of per-thread dot products).  Measured 24 us per launch at
-    // K = 64, D = 24 (ncu: 51 k cycles, issue slots 13 % used, half of the warp samples waiting at a barrier) — the same as a first
-    // version with per-thread dot products and two barriers per column, so the remaining time is not in those chains.
+    // Latency-bound by construction (one CTA works through a 24 x 24 factorisation, 64 CTAs on 148 SMs; dependent FP64 operations
+    // cost ~45 cycles each here — build-time phase stamps, GMM_FIN_PROF): one global round trip (the cluster's statistics row is staged
+    // in shared memory), a THREAD PER MATRIX ELEMENT so that the rank-1 update of a column / row step is one pass (three serial passes of
+    // 256 threads cost 880 cycles per column), one barrier per column of the factorisation and per row of the triangular inverse, and a
+    // reciprocal square root of the pivot from the FP32 approximation + one Newton step (relative error ~1e-13: the results are stored as floats).
+#ifdef GMM_FIN_PROF
+    long long fin_t[10];
+#endif
     using C = ECfg<D>;
+    constexpr int T = FinCfg<D>::T, NW = FinCfg<D>::NW;
     constexpr int F = 1 + D + D * (D + 1) / 2;
     constexpr int LD = D + 1;
     const int k = blockIdx.x, tid = threadIdx.x;
@@ -1307,17 +1319,18 @@ finalize_params_kernel(const double* __restrict__ stats, const float* __restrict
     if (k >= K) {                                              // padding: never wins the log-sum-exp, all-zero operand rows
         if (tid == 0) { ckp[0] = -1e30f; ckp[64] = 0.f; }
         if (k < kp)
-            for (int idx = tid; idx < D * C::NCHKB; idx += 256) *reinterpret_cast<uint4*>(rowp(idx / C::NCHKB, idx % C::NCHKB)) = make_uint4(0u, 0u, 0u, 0u);
+            for (int idx = tid; idx < D * C::NCHKB; idx += T) *reinterpret_cast<uint4*>(rowp(idx / C::NCHKB, idx % C::NCHKB)) = make_uint4(0u, 0u, 0u, 0u);
         return;
     }
-    __shared__ double sS[F + 3], sA[D][LD], sU[D][LD], sW[D][LD], srd[D], spiv[D], sdm[D], sscale[D], svd[D], sredd[8];
-    __shared__ float swr[D][LD], sredf[8];
+    FIN_STAMP(0);
+    __shared__ double sS[F + 3], sA[D][LD], sU[D][LD], sW[D][LD], srd[D], spiv[D], sdm[D], sscale[D], svd[D], sredd[NW];
+    __shared__ float swr[D][LD], sredf[NW];
     __shared__ int sbad;
     // ---- stage: the statistics row, the S0 of every cluster (pi), shift / scale ----
     const double* s = stats + (size_t)k * F;
-    for (int f = tid; f < F; f += 256) sS[f] = s[f];
+    for (int f = tid; f < F; f += T) sS[f] = s[f];
     double part = 0.0;
-    for (int kk = tid; kk < K; kk += 256) part += (double)(float)stats[(size_t)kk * F];
+    for (int kk = tid; kk < K; kk += T) part += (double)(float)stats[(size_t)kk * F];
     double shift_d = 0.0;
     if (tid < D) { shift_d = (double)shift_f[tid]; sscale[tid] = scale[tid]; }
     const float av = avgvar[k];
@@ -1328,6 +1341,7 @@ finalize_params_kernel(const double* __restrict__ stats, const float* __restrict
     if ((tid & 31) == 0) sredd[tid >> 5] = part;
     if (tid == 0) sbad = 0;
     __syncthreads();
+    FIN_STAMP(1);
     const double S0 = sS[0];
     const float Nf = (float)S0;
     if (k == 0 && tid == 0) {
@@ -1338,7 +1352,7 @@ finalize_params_kernel(const double* __restrict__ stats, const float* __restrict
     // ---- pi (compute_pi, gaussian_kernel.cu:172-193), means (gaussian.cu:611-622), R (:663-679, gaussian_kernel.cu:658-675) ----
     double sumN = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) sumN += sredd[w];
+    for (int w = 0; w < NW; w++) sumN += sredd[w];
     const float pik = Nf < 0.5f ? 1e-10f : (float)((double)Nf / sumN);
     if (tid < D) {
         const double m = (S0 != 0.0) ? sS[1 + tid] / S0 : 0.0;
@@ -1349,7 +1363,7 @@ finalize_params_kernel(const double* __restrict__ stats, const float* __restrict
     {
         float* R = set + pset_off_R(Kmax, D) + (size_t)k * D * D;
         const double inv = 1.0 / (double)Nf;
-        for (int idx = tid; idx < D * D; idx += 256) {
+        for (int idx = tid; idx < D * D; idx += T) {
             const int i = idx / D, j = idx % D;
             if (j > i) continue;
             float v;
@@ -1367,16 +1381,18 @@ finalize_params_kernel(const double* __restrict__ stats, const float* __restrict
         }
     }
     __syncthreads();
+    FIN_STAMP(2);
     // ---- R = U U^T from the last column: ONE barrier per column.  sA keeps the unscaled trailing block (upper triangle),
     //      the scaled column goes to sU, its reciprocal pivot to srd, the pivot's square to spiv (ln det) ----
     bool ok = true;
     for (int j = D - 1; j >= 0; j--) {
         const double d = sA[j][j];
         if (!(d > 0.0) || !isfinite(d)) { ok = false; break; }    // the same value in every thread
-        const double rp = rsqrt(d), invd = rp * rp;
+        const double y0 = (d > 1e-30 && d < 1e30) ? (double)rsqrtf((float)d) : rsqrt(d);   // 22 bits (float range), else the full routine
+        const double rp = y0 * fma(-0.5 * d, y0 * y0, 1.5), invd = rp * rp;
         if (tid < j) sU[tid][j] = sA[tid][j] * rp;
         else if (tid == j) { srd[j] = rp; spiv[j] = d; }
-        for (int idx = tid; idx < D * D; idx += 256) {            // (i, m) with i <= m < j:  A[i][m] -= A[i][j] A[m][j] / d
+        for (int idx = tid; idx < D * D; idx += T) {            // (i, m) with i <= m < j:  A[i][m] -= A[i][j] A[m][j] / d
             const int i = idx / D, m = idx % D;
             if (i <= m && m < j) sA[i][m] -= sA[i][j] * sA[m][j] * invd;
         }
@@ -1386,12 +1402,13 @@ finalize_params_kernel(const double* __restrict__ stats, const float* __restrict
         if (tid == 0) { atomicCAS(&bad[0], -1, iter); atomicMax(&bad[1], 1); }
         return;
     }
+    FIN_STAMP(3);
     // ---- W = U^-1 (upper triangular), row by row from the bottom, ONE barrier per row: when row m is final, every row i < m
     //      takes its term U[i][m] W[m][j]; the thread that completes row m - 1 scales it (W[i][j] = -(sum) / U[i][i]) ----
     if (tid < D) sW[tid][tid] = srd[tid];
     __syncthreads();
     for (int m = D - 1; m >= 1; m--) {
-        for (int idx = tid; idx < D * D; idx += 256) {
+        for (int idx = tid; idx < D * D; idx += T) {
             const int i = idx / D, j = idx % D;
             if (i < m && j >= m) {
                 double acc = sW[i][j] + sU[i][m] * sW[m][j];
@@ -1401,10 +1418,11 @@ finalize_params_kernel(const double* __restrict__ stats, const float* __restrict
         }
         __syncthreads();
     }
+    FIN_STAMP(4);
     // ---- Rinv = W^T W, ln det, constant (gaussian_kernel.cu:241), N, pi; operand rows: W'[d][j] = W[d][j] * scale_j, v = -W (mu - shift) ----
     {
         float* Ri = set + pset_off_Rinv(Kmax, D) + (size_t)k * D * D;
-        for (int idx = tid; idx < D * D; idx += 256) {
+        for (int idx = tid; idx < D * D; idx += T) {
             const int i = idx / D, j = idx % D;
             if (j < i) continue;
             double v = 0.0;
@@ -1413,8 +1431,9 @@ finalize_params_kernel(const double* __restrict__ stats, const float* __restrict
             Ri[i * D + j] = (float)v; Ri[j * D + i] = (float)v;
         }
     }
+    FIN_STAMP(5);
     float amax = 0.f;
-    for (int idx = tid; idx < D * D; idx += 256) {
+    for (int idx = tid; idx < D * D; idx += T) {
         const int d = idx / D, j = idx % D;
         const float w = (j >= d) ? (float)(sW[d][j] * sscale[j]) : 0.f;
         swr[d][j] = w;
@@ -1438,12 +1457,13 @@ finalize_params_kernel(const double* __restrict__ stats, const float* __restrict
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     if ((tid & 31) == 0) sredf[tid >> 5] = amax;
     __syncthreads();
+    FIN_STAMP(6);
     const double ld = 0.5 * sredd[0];                          // sum ln U_jj
     const float cst = (float)(-D * 0.5 * log(2.0 * 3.1415926535897931) - 0.5 * (2.0 * ld));
     if (tid == 0) { set[k] = Nf; set[Kmax + k] = pik; set[2 * (size_t)Kmax + k] = cst; }
     amax = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; w++) amax = fmaxf(amax, sredf[w]);
+    for (int w = 0; w < NW; w++) amax = fmaxf(amax, sredf[w]);
     if (!isfinite(amax)) {
         if (tid == 0) { atomicCAS(&bad[0], -1, iter); atomicMax(&bad[1], 2); }
         return;
@@ -1451,7 +1471,7 @@ finalize_params_kernel(const double* __restrict__ stats, const float* __restrict
     // per-cluster power-of-two scale: the largest operand entry lands in [2^12, 2^13) (see bimg_cluster)
     int e2 = amax > 0.f ? 12 - ilogbf(amax) : 0;
     e2 = e2 > 40 ? 40 : (e2 < -40 ? -40 : e2);
-    for (int idx = tid; idx < D * C::CP; idx += 256) {
+    for (int idx = tid; idx < D * C::CP; idx += T) {
         const int d = idx / C::CP, c = idx % C::CP;
         uint32_t hi[4], lo[4];
 #pragma unroll
@@ -1481,6 +1501,12 @@ finalize_params_kernel(const double* __restrict__ stats, const float* __restrict
         ckp[64] = (float)ldexp(-0.5 * 1.4426950408889634, -2 * e2);
     }
     __syncthreads();
+    FIN_STAMP(7);
+#ifdef GMM_FIN_PROF
+    if (k == 0 && tid == 0)
+        printf("fin phases (cycles): stage %lld  means+R %lld  cholesky %lld  inverse %lld  Rinv %lld  rows+v+log %lld  operand %lld\n",
+               fin_t[1] - fin_t[0], fin_t[2] - fin_t[1], fin_t[3] - fin_t[2], fin_t[4] - fin_t[3], fin_t[5] - fin_t[4], fin_t[6] - fin_t[5], fin_t[7] - fin_t[6]);
+#endif
     if (tid == 0 && sbad) { atomicCAS(&bad[0], -1, iter); atomicMax(&bad[1], sbad); }
 }
 
@@ -1503,7 +1529,7 @@ int tc_launch_finalize(TcState* t, int K, const double* d_stats, const float* d_
     if (!tc_finalize_supported(t, K)) return fail(GMM_ERR_STATE, "device-side finalisation not available for this state");
     const int kp = tc_params_padded(t, K);
     const int grid = ((K + 63) / 64) * 64;                     // whole passes: the padding clusters of the last pass get their constants
-#define GMM_FIN(d) finalize_params_kernel<d><<<grid, 256, 0, stream>>>(d_stats, d_avgvar, t->d_shift_f, t->d_scale, d_set, t->Kmax, K, kp, \
+#define GMM_FIN(d) finalize_params_kernel<d><<<grid, FinCfg<d>::T, 0, stream>>>(d_stats, d_avgvar, t->d_shift_f, t->d_scale, d_set, t->Kmax, K, kp, \
                                                                      t->d_bimg, t->d_ck, d_ll, d_bad, iter, fault_iter)
     switch (t->D) {
         case 8: GMM_FIN(8); break;
