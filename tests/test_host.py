@@ -257,3 +257,21 @@ def test_host_worker_team_selftest(pkg):
     lib = pkg.load_library()
     for threads, jobs, n in ((1, 50, 7), (2, 3000, 64), (8, 3000, 80), (16, 1500, 5)):
         assert lib.gmm_host_pool_selftest(threads, jobs, n) == 0, lib.gmm_last_error()
+
+
+def test_every_runtime_option_is_documented():
+    """Every key gmm_set_option accepts (csrc/gmm_api.cu) is described in the C header and in INTEGRATION.md."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "cuda-gmm-mpi_b200", "csrc", "gmm_api.cu")).read()
+    body = src[src.index("int gmm_set_option("):]
+    body = body[:body.index("\n}\n")]
+    keys = set(re.findall(r'k == "([a-z_]+)"', body))
+    assert {"path", "finalize", "allreduce", "host_threads", "profile"} <= keys
+    header = open(os.path.join(root, "include", "gmm.h")).read()
+    integ = open(os.path.join(root, "INTEGRATION.md")).read()
+    for k in keys:
+        assert f'"{k}"' in header, f"option {k} is not documented in include/gmm.h"
+        if k != "finalize_fault_iter":                 # test hook: header only
+            assert f"`{k}`" in integ, f"option {k} is not documented in INTEGRATION.md"
