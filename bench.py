@@ -5,9 +5,10 @@
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (N>1)
 
 A "step" is one pass of the EM loop body of the reference (gaussian.cu:532-755):
-M-step statistics -> all-reduce of the packed statistics -> host normalisation +
-DxD inversions + constants -> parameter upload -> E-step (responsibilities +
-log-likelihood), on the synthetic workload of BASELINE.json config 3
+M-step statistics -> all-reduce of the packed statistics -> normalisation +
+DxD inversions + constants + E-step operand (one device kernel; option "finalize" = 0
+/ GMM_FINALIZE=host: on the host with one D2H and one H2D) -> E-step (responsibilities
++ log-likelihood), on the synthetic workload of BASELINE.json config 3
 (N=10M, D=24, K=64; config 4 shards the same 10M events over N GPUs = strong
 scaling).  `value` is measured with the events resident in HBM: a block of exactly
 K steps is timed (barrier + synchronize on both sides, device clock, max over
